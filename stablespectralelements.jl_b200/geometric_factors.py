@@ -1,0 +1,264 @@
+"""Geometric factors and the ``SpatialDiscretization`` bundle (host-side setup).
+
+Mirrors /root/reference/src/SpatialDiscretizations/mesh.jl:213-509 (``metrics``,
+``GeometricFactors`` for ``ExactMetrics`` and ``ConservativeCurlMetrics``) and
+SpatialDiscretizations.jl:248-423 (``GeometricFactors`` struct, ``SpatialDiscretization``
+constructors with Jacobian projection, ``apply_reference_mapping``, self-checks).  Everything
+is vectorised over elements; arrays keep the reference's index order with the element index
+last, stored as C-contiguous NumPy arrays of shape (N_e, ...) *reversed* -- see ``layout``
+below -- so that a flat view equals Julia's column-major memory.
+
+Layout convention used throughout the host package: a Julia array ``A[i1, i2, ..., k]`` is a
+NumPy array ``A[k, ..., i2, i1]`` (C order), i.e. identical bytes.  E.g. ``J_q`` is (N_e, N_q),
+``Lambda_q`` is (N_e, d_n, d_m, N_q) for Julia's ``Λ_q[i, m, n, k]``, ``nJf`` is (N_e, N_f, d).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import nodes as nd
+from . import polynomials as poly
+from .mesh import MeshData
+from .reference_approximation import (Hex, NoMapping, ReferenceApproximation, ReferenceMapping,
+                                      RefElemData, Tet, Tri, reference_vertices, vandermonde)
+
+
+class ExactMetrics:
+    pass
+
+
+class ConservativeCurlMetrics:
+    pass
+
+
+ChanWilcoxMetrics = ConservativeCurlMetrics
+
+
+@dataclass
+class GeometricFactors:
+    """SpatialDiscretizations.jl:248-283 (memory-identical layouts, see module docstring)."""
+    J_q: np.ndarray        # (N_e, N_q)
+    Lambda_q: np.ndarray   # (N_e, d[n], d[m], N_q)   == Julia Λ_q[i, m, n, k]
+    J_f: np.ndarray        # (N_e, N_f)
+    nJf: np.ndarray        # (N_e, N_f, d)            == Julia nJf[m, i, k]
+    n_ref: np.ndarray      # (num_faces, d) reference normal of each face (nrstJ at first node)
+
+    def nJq(self):
+        """Julia nJq[n, f, i, k] = Σ_m Λ_q[i,m,n,k] n_ref[m,f] (mesh.jl:266-271) as
+        (N_e, N_q, num_faces, d)."""
+        return np.einsum("knmi,fm->kifn", self.Lambda_q, self.n_ref)
+
+
+def _metrics_from_dxdr(dxdr):
+    """mesh.jl:213-229.  dxdr[..., m, n] = ∂x_m/∂ξ_n ; returns J, Λ[..., l, m] = J ∂ξ_l/∂x_m."""
+    d = dxdr.shape[-1]
+    if d == 1:
+        return dxdr[..., 0, 0].copy(), np.ones_like(dxdr)
+    if d == 2:
+        J = dxdr[..., 0, 0] * dxdr[..., 1, 1] - dxdr[..., 0, 1] * dxdr[..., 1, 0]
+        L = np.empty_like(dxdr)
+        L[..., 0, 0] = dxdr[..., 1, 1]
+        L[..., 0, 1] = -dxdr[..., 0, 1]
+        L[..., 1, 0] = -dxdr[..., 1, 0]
+        L[..., 1, 1] = dxdr[..., 0, 0]
+        return J, L
+    a = dxdr
+    L = np.empty_like(a)
+    # adjugate (= J * inverse)
+    L[..., 0, 0] = a[..., 1, 1] * a[..., 2, 2] - a[..., 1, 2] * a[..., 2, 1]
+    L[..., 0, 1] = a[..., 0, 2] * a[..., 2, 1] - a[..., 0, 1] * a[..., 2, 2]
+    L[..., 0, 2] = a[..., 0, 1] * a[..., 1, 2] - a[..., 0, 2] * a[..., 1, 1]
+    L[..., 1, 0] = a[..., 1, 2] * a[..., 2, 0] - a[..., 1, 0] * a[..., 2, 2]
+    L[..., 1, 1] = a[..., 0, 0] * a[..., 2, 2] - a[..., 0, 2] * a[..., 2, 0]
+    L[..., 1, 2] = a[..., 0, 2] * a[..., 1, 0] - a[..., 0, 0] * a[..., 1, 2]
+    L[..., 2, 0] = a[..., 1, 0] * a[..., 2, 1] - a[..., 1, 1] * a[..., 2, 0]
+    L[..., 2, 1] = a[..., 0, 1] * a[..., 2, 0] - a[..., 0, 0] * a[..., 2, 1]
+    L[..., 2, 2] = a[..., 0, 0] * a[..., 1, 1] - a[..., 0, 1] * a[..., 1, 0]
+    J = a[..., 0, 0] * L[..., 0, 0] + a[..., 0, 1] * L[..., 1, 0] + a[..., 0, 2] * L[..., 2, 0]
+    return J, L
+
+
+def _n_ref(re: RefElemData):
+    nfaces = re.element_type.num_faces
+    npf = len(re.wf) // nfaces
+    return np.array([[re.nrstJ[m][npf * f] for m in range(re.dim)] for f in range(nfaces)])
+
+
+def _facet_normals(Lambda_f, re: RefElemData):
+    """nJf[m,i] = Σ_n Λ_f[i,n,m] nrstJ[n][i]; J_f = |nJf| (mesh.jl:273-281).
+    Lambda_f: (N_e, N_f, d[l], d[m])."""
+    nr = np.stack(re.nrstJ, axis=1)                      # (N_f, d)
+    nJf = np.einsum("kinm,in->kim", Lambda_f, nr)
+    J_f = np.sqrt(np.sum(nJf ** 2, axis=2))
+    return nJf, J_f
+
+
+def geometric_factors_exact(mesh: MeshData, re: RefElemData) -> GeometricFactors:
+    """mesh.jl:231-284."""
+    d = re.dim
+    N_e = mesh.N_e
+    N_q, N_f = re.Vq.shape[0], re.Vf.shape[0]
+    dq = np.empty((N_e, N_q, d, d))
+    df = np.empty((N_e, N_f, d, d))
+    for m in range(d):
+        for n in range(d):
+            dxdr = re.Drst[n] @ mesh.xyz[m]              # (N_map, N_e)
+            dq[:, :, m, n] = (re.Vq @ dxdr).T
+            df[:, :, m, n] = (re.Vf @ dxdr).T
+    J_q, Lq = _metrics_from_dxdr(dq)                      # Lq (N_e, N_q, l, m)
+    _, Lf = _metrics_from_dxdr(df)
+    nJf, J_f = _facet_normals(Lf, re)
+    Lambda_q = np.ascontiguousarray(Lq.transpose(0, 3, 2, 1))   # (N_e, n=m_idx2, m=l, N_q)
+    return GeometricFactors(np.ascontiguousarray(J_q), Lambda_q, J_f, nJf, _n_ref(re))
+
+
+def _curl_metrics_3d(x, y, z, Dr, Ds, Dt):
+    """StartUpDG ``geometric_factors(x,y,z,Dr,Ds,Dt)`` (un-vendored): conservative curl form of
+    Kopriva (2006); returns the 9 scaled metric terms (as Λ[l][m] = J ∂ξ_l/∂x_m) and J."""
+    xr, xs, xt = Dr @ x, Ds @ x, Dt @ x
+    yr, ys, yt = Dr @ y, Ds @ y, Dt @ y
+    zr, zs, zt = Dr @ z, Ds @ z, Dt @ z
+
+    def curl(Fr, Fs, Ft):
+        return (Dt @ Fs - Ds @ Ft, Dr @ Ft - Dt @ Fr, Ds @ Fr - Dr @ Fs)
+
+    rxJ, sxJ, txJ = curl(yr * z, ys * z, yt * z)
+    ryJ, syJ, tyJ = (-c for c in curl(xr * z, xs * z, xt * z))
+    rzJ, szJ, tzJ = (-c for c in curl(yr * x, ys * x, yt * x))
+    J = xr * (ys * zt - zs * yt) - yr * (xs * zt - zs * xt) + zr * (xs * yt - ys * xt)
+    return ((rxJ, ryJ, rzJ), (sxJ, syJ, szJ), (txJ, tyJ, tzJ)), J
+
+
+def geometric_factors_curl(mesh: MeshData, re: RefElemData) -> GeometricFactors:
+    """mesh.jl:286-509 (2-D, Hex and Tet variants)."""
+    d = re.dim
+    elem = re.element_type
+    N_e = mesh.N_e
+    if d == 1:
+        return geometric_factors_exact(mesh, re)
+    if d == 2:
+        x, y = mesh.xyz
+        Dr, Ds = re.Drst
+        xr, xs, yr, ys = Dr @ x, Ds @ x, Dr @ y, Ds @ y
+        J = -xs * yr + xr * ys
+        L = ((ys, -xs), (-yr, xr))               # L[l][m]: rxJ ryJ / sxJ syJ
+        Vq, Vf = re.Vq, re.Vf
+        J_q = (Vq @ J).T
+    elif isinstance(elem, Hex):
+        L, J = _curl_metrics_3d(*mesh.xyz, *re.Drst)
+        Vq, Vf = re.Vq, re.Vf
+        J_q = (Vq @ J).T
+    elif isinstance(elem, Tet):
+        N = re.N
+        r1, s1, t1 = nd.nodes_tet(N + 1)
+        V1, Vr1, Vs1, Vt1 = poly.simplex_basis_3d(N + 1, r1, s1, t1, grad=True)
+        N_to_Np1 = np.linalg.solve(re.VDM.T, vandermonde(elem, N, r1, s1, t1).T).T
+        Np1_to_N = np.linalg.solve(V1.T, vandermonde(elem, N + 1, *re.rst).T).T
+        Vq = re.Vq @ Np1_to_N
+        Vf = re.Vf @ Np1_to_N
+        _, J = _curl_metrics_3d(*mesh.xyz, *re.Drst)
+        J_q = (re.Vq @ J).T
+        D1 = tuple(np.linalg.solve(V1.T, g.T).T for g in (Vr1, Vs1, Vt1))
+        L, _ = _curl_metrics_3d(*(N_to_Np1 @ c for c in mesh.xyz), *D1)
+    else:
+        raise TypeError(elem)
+    N_q, N_f = Vq.shape[0], Vf.shape[0]
+    Lambda_q = np.empty((N_e, d, d, N_q))         # [k, n, m, i]  (m = ξ index, n = x index)
+    Lf = np.empty((N_e, N_f, d, d))               # [k, i, l, m]
+    for l in range(d):
+        for m in range(d):
+            Lambda_q[:, m, l, :] = (Vq @ L[l][m]).T
+            Lf[:, :, l, m] = (Vf @ L[l][m]).T
+    nJf, J_f = _facet_normals(Lf, re)
+    return GeometricFactors(np.ascontiguousarray(J_q), Lambda_q, J_f, nJf, _n_ref(re))
+
+
+def make_geometric_factors(mesh, re, metric_type=None) -> GeometricFactors:
+    if metric_type is None or isinstance(metric_type, ExactMetrics):
+        return geometric_factors_exact(mesh, re)
+    return geometric_factors_curl(mesh, re)
+
+
+def project_jacobian(J_q, V, W):
+    """SpatialDiscretizations.jl:311-318: L2 projection of J onto the solution space."""
+    VDM = V.to_dense()
+    proj = VDM @ np.linalg.solve(VDM.T @ (W[:, None] * VDM), VDM.T * W[None, :])
+    return np.ascontiguousarray(J_q @ proj.T)
+
+
+@dataclass
+class SpatialDiscretization:
+    """SpatialDiscretizations.jl:292-393 (without plotting nodes / dense mass matrices)."""
+    mesh: MeshData
+    reference_approximation: ReferenceApproximation
+    geometric_factors: GeometricFactors
+
+    @property
+    def N_e(self):
+        return self.mesh.N_e
+
+    @property
+    def dim(self):
+        return self.reference_approximation.dim
+
+
+def make_spatial_discretization(mesh: MeshData, ra: ReferenceApproximation, metric_type=None,
+                                project_jacobian_flag: Optional[bool] = None
+                                ) -> SpatialDiscretization:
+    """``SpatialDiscretization(mesh, ra[, metric_type]; project_jacobian=true)``.
+
+    ExactMetrics projects the Jacobian by default; the ChanWilcox constructor never does
+    (SpatialDiscretizations.jl:334-393)."""
+    exact = metric_type is None or isinstance(metric_type, ExactMetrics)
+    gf = make_geometric_factors(mesh, ra.reference_element, metric_type)
+    if project_jacobian_flag is None:
+        project_jacobian_flag = exact
+    if exact and project_jacobian_flag:
+        gf.J_q = project_jacobian(gf.J_q, ra.V, ra.W)
+    return SpatialDiscretization(mesh, ra, gf)
+
+
+def apply_reference_mapping(gf: GeometricFactors, reference_mapping) -> np.ndarray:
+    """SpatialDiscretizations.jl:396-412: Λ_η[i,m,n,k] = Σ_l Λ_ref[i,m,l] Λ_q[i,l,n,k]/J_ref[i];
+    returns the (N_e, d[n], d[m], N_q) array."""
+    if isinstance(reference_mapping, NoMapping):
+        return gf.Lambda_q
+    Lr, Jr = reference_mapping.Lambda_ref, reference_mapping.J_ref
+    return np.einsum("iml,knli->knmi", Lr / Jr[:, None, None], gf.Lambda_q)
+
+
+def check_normals(sd: SpatialDiscretization):
+    """SpatialDiscretizations.jl:426-432."""
+    nJf = sd.geometric_factors.nJf
+    flat = nJf.reshape(-1, nJf.shape[2])
+    mp = sd.mesh.mapP.T.reshape(-1)                       # [k, j] -> j + N_f k
+    return np.max(np.abs(flat + flat[mp]))
+
+
+def check_facet_nodes(sd: SpatialDiscretization):
+    """SpatialDiscretizations.jl:434-439 (modulo the period)."""
+    mesh = sd.mesh
+    err = 0.0
+    mp = mesh.mapP.ravel(order="F")
+    for m in range(mesh.dim):
+        L = mesh.limits[m][1] - mesh.limits[m][0]
+        xf = mesh.xyzf[m].ravel(order="F")
+        dlt = (xf - xf[mp] + 0.5 * L) % L - 0.5 * L
+        err = max(err, float(np.max(np.abs(dlt))))
+    return err
+
+
+def check_metric_identities(sd: SpatialDiscretization):
+    """Discrete free-stream preservation: max |Σ_l D_ξl Λ_q[:, l, m]| over elements."""
+    from .reference_approximation import reference_derivative_operators
+    ra = sd.reference_approximation
+    D_xi = reference_derivative_operators(ra.D, ra.reference_mapping)
+    L = sd.geometric_factors.Lambda_q                      # (k, n, m, i)
+    out = 0.0
+    for n in range(sd.dim):
+        acc = sum(np.einsum("ij,kj->ki", D_xi[l], L[:, n, l, :]) for l in range(sd.dim))
+        out = max(out, float(np.max(np.abs(acc))))
+    return out
