@@ -1,0 +1,161 @@
+/*
+ * sse_b200.h -- C ABI of libsse_b200.so, the B200 (sm_100a) residual engine for
+ * StableSpectralElements.jl.
+ *
+ * One entry point per thing the reference's hot path does (file:line cite the reference,
+ * relative to /root/reference/src/):
+ *
+ *   sse_create            <- Solver(...) constructors, Solvers/Solvers.jl:287-377, including the
+ *                            operator bundles of Solvers/operators.jl:1-225 (halfWΛ, n_f, BJf, WJ,
+ *                            S, C are derived on the device side from the arrays passed here) and
+ *                            the mass solvers of Solvers/mass_matrix.jl:1-136
+ *   sse_residual          <- semi_discrete_residual!(dudt, u, solver, t), Solvers/Solvers.jl:455-570
+ *   sse_nodal_values      <- loop A: nodal_values!/entropy_projection!,
+ *                            Solvers/standard_form_first_order.jl:1-14,
+ *                            Solvers/flux_differencing_form.jl:171-292
+ *   sse_time_derivative   <- loop B (and A2 for second-order PDEs): time_derivative!,
+ *                            auxiliary_variable!, standard_form_first_order.jl:16-94,
+ *                            standard_form_second_order.jl:3-75, flux_differencing_form.jl:294-347
+ *   sse_rk_stage/_step    <- the low-storage 2N Runge-Kutta update OrdinaryDiffEq applies around
+ *                            the residual (test/test_driver.jl:77-83), fused into the residual
+ *                            epilogue so the state never leaves the device
+ *   sse_halo_*            <- (new) facet-trace halo for element-sharded multi-GPU runs; the only
+ *                            inter-element read of the reference is u_f[CI[mapP[:,k]],:]
+ *                            (flux_differencing_form.jl:312-313)
+ *
+ * Conventions: all arrays are Float64 in the reference's (Julia, column-major) memory layout;
+ * integer indices are 0-based; every function returns 0 on success and a negative code on
+ * failure with a message available from sse_last_error().  Nothing throws across the ABI.
+ * One in-flight call per handle (like the reference's Solver, whose scratch is shared).
+ */
+#ifndef SSE_B200_H
+#define SSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sse_handle sse_handle;
+
+enum sse_law { SSE_LAW_ADVECTION = 0, SSE_LAW_BURGERS = 1, SSE_LAW_EULER = 2,
+               SSE_LAW_ADVECTION_DIFFUSION = 3, SSE_LAW_VISCOUS_BURGERS = 4 };
+enum sse_form { SSE_FORM_STANDARD = 0, SSE_FORM_FLUX_DIFFERENCING = 1 };
+enum sse_strategy { SSE_REFERENCE_OPERATOR = 0, SSE_PHYSICAL_OPERATOR = 1 };
+enum sse_inviscid_flux { SSE_FLUX_LAX_FRIEDRICHS = 0, SSE_FLUX_CENTRAL = 1,
+                         SSE_FLUX_ENTROPY_CONSERVATIVE = 2 };
+enum sse_two_point_flux { SSE_TWO_POINT_CONSERVATIVE = 0, SSE_TWO_POINT_ENTROPY_CONSERVATIVE = 1 };
+enum sse_v_kind { SSE_V_IDENTITY = 0, SSE_V_WARPED = 1, SSE_V_DENSE = 2 };
+enum sse_mass_solver { SSE_MASS_DIAGONAL = 0, SSE_MASS_WEIGHT_ADJUSTED = 1, SSE_MASS_CHOLESKY = 2 };
+enum sse_where { SSE_HOST = 0, SSE_DEVICE = 1 };
+
+/* Mirrors the type parameters of Solver{...} (Solvers.jl:259-272) as plain enums. */
+typedef struct {
+  int32_t dim;            /* d                                                         */
+  int32_t N_p, N_q, N_f;  /* modes / volume nodes / facet nodes per element            */
+  int32_t N_c;            /* conservative variables                                    */
+  int32_t num_faces;      /* faces per element (N_f / num_faces nodes on each)         */
+  int64_t N_e;            /* local elements                                            */
+  int64_t N_halo;         /* extra trace slots (facet nodes) owned by other ranks      */
+  int32_t law;            /* enum sse_law                                              */
+  double  a[3];           /* advection velocity / Burgers direction                    */
+  double  b;              /* diffusion coefficient                                     */
+  double  gamma;          /* Euler specific-heat ratio                                 */
+  int32_t form;           /* enum sse_form                                             */
+  int32_t strategy;       /* enum sse_strategy                                         */
+  int32_t inviscid_flux;  /* enum sse_inviscid_flux                                    */
+  double  half_lambda;    /* LaxFriedrichsNumericalFlux.halfλ (ConservationLaws.jl:52) */
+  int32_t two_point_flux; /* enum sse_two_point_flux (flux-differencing form only)     */
+  int32_t v_kind;         /* enum sse_v_kind                                           */
+  int32_t r_is_selection; /* R is a SelectionMap (diag-E): no facet correction         */
+  int32_t mass_solver;    /* enum sse_mass_solver                                      */
+  int32_t device;         /* CUDA device ordinal                                       */
+} sse_config;
+
+/* Reference-element operators (ReferenceApproximation, SpatialDiscretizations.jl:186-246).
+ * Sparse operators are CSR (rowptr has rows+1 entries).  Unused pointers may be NULL. */
+typedef struct {
+  /* V: (N_q x N_p).  DENSE: row-major matrix.  WARPED: tables of
+   * MatrixFreeOperators/warped_product_{2d,3d}.jl built by tensor_simplex.jl:84-140:
+   * A[a1][b1] (n x n), B[a2][b1][b2] (n^3), C[a3][b1][b2][b3] (n^4, 3-D only),
+   * sigma_i[b1][b2]([b3]) (-1 where unused), all C-ordered, n = p + 1 nodes per direction. */
+  const double*  V_dense;
+  int32_t        n1d;
+  const double*  warp_A;
+  const double*  warp_B;
+  const double*  warp_C;
+  const int32_t* sigma_i;
+  /* R: (N_f x N_q) interpolation/extrapolation to facet nodes */
+  const int32_t* R_rowptr; const int32_t* R_col; const double* R_val;
+  /* D_eta[m]: (N_q x N_q) derivative operators in (collapsed) reference coordinates */
+  const int32_t* D_rowptr[3]; const int32_t* D_col[3]; const double* D_val[3];
+  const double*  W;            /* N_q volume quadrature weights   */
+  const double*  B;            /* N_f facet quadrature weights    */
+  const double*  Lambda_ref;   /* Julia Λ_ref[i,l,m] (N_q,d,d) or NULL (NoMapping)      */
+  const double*  J_ref;        /* N_q or NULL                                           */
+  const double*  n_ref;        /* (num_faces x d) row-major reference face normals      */
+  const double*  Minv;         /* (N_p x N_p) row-major M^-1 of WeightAdjustedSolver, or NULL = I */
+} sse_operators;
+
+/* GeometricFactors (SpatialDiscretizations.jl:248-283), Julia memory layout. */
+typedef struct {
+  const double* J_q;       /* (N_q, N_e)                                                */
+  const double* Lambda_q;  /* (N_q, d, d, N_e):  J dξ_l/dx_m at [i, l, m, k]            */
+  const double* J_f;       /* (N_f, N_e)                                                */
+  const double* nJf;       /* (d, N_f, N_e)                                             */
+  /* PhysicalOperators (operators.jl:85-164), only for SSE_PHYSICAL_OPERATOR:             */
+  const double* VOL;       /* (N_q, N_p, d, N_e) i.e. VOL[k][m] stored transposed (row-major N_p x N_q) */
+  const double* FAC;       /* (N_f, N_p, N_e)    i.e. FAC[k] row-major N_p x N_f        */
+  const double* Minv_elem; /* (N_p, N_p, N_e) per-element inverse mass matrix, SSE_MASS_CHOLESKY */
+} sse_geometry;
+
+const char* sse_last_error(void);
+int  sse_version(void);
+
+/* mapP: (N_f, N_e) 0-based linear index j' + N_f*k' into the (N_f, N_e [+halo]) trace array;
+ * indices >= N_f*N_e address halo slots filled by sse_halo_unpack / the exchange. */
+int sse_create(const sse_config* cfg, const sse_operators* ops, const sse_geometry* geo,
+               const int64_t* mapP, sse_handle** out);
+int sse_destroy(sse_handle* h);
+
+/* semi_discrete_residual!(dudt, u, solver, t): u, dudt are (N_p, N_c, N_e).
+ * where = SSE_HOST: pageable/pinned host pointers, copies included;
+ * where = SSE_DEVICE: device pointers on cfg.device (no copies). */
+int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int where);
+
+/* The two loops separately (element-sharded runs exchange the halo in between). */
+int sse_nodal_values(sse_handle* h, const double* u_dev);
+int sse_time_derivative(sse_handle* h, double* dudt_dev);
+
+/* Device-resident state and fused low-storage (2N) Runge-Kutta:
+ *   k <- a*k + dt*R(u);  u <- u + b*k   (evaluated in the residual kernel's epilogue). */
+int sse_set_state(sse_handle* h, const double* u_host);
+int sse_get_state(sse_handle* h, double* u_host);
+int sse_state_ptr(sse_handle* h, double** u_dev, double** dudt_dev);
+int sse_rk_stage(sse_handle* h, double a, double b, double dt);
+int sse_rk_step_ck54(sse_handle* h, double dt);   /* Carpenter-Kennedy (5,4), 5 fused stages */
+
+/* Halo of facet traces for element-sharded runs.  send_idx: n_send linear indices (j + N_f*k)
+ * of local trace nodes to pack; the packed buffer holds N_c doubles per index, variable-major
+ * ([c][n]).  Received values are unpacked into halo slots [0, N_halo). */
+int sse_halo_setup(sse_handle* h, const int64_t* send_idx, int64_t n_send);
+int sse_halo_buffers(sse_handle* h, double** send_dev, double** recv_dev, int64_t* n_send,
+                     int64_t* n_recv);
+int sse_halo_pack(sse_handle* h);      /* traces -> send buffer (after sse_nodal_values)     */
+int sse_halo_unpack(sse_handle* h);    /* recv buffer -> halo trace slots                     */
+
+/* Streams / timing / introspection. */
+int sse_sync(sse_handle* h);
+void* sse_stream(sse_handle* h);                         /* cudaStream_t the kernels run on */
+/* Runs `reps` residuals on the device-resident state, timed with CUDA events on the
+ * library's stream; ms[0] = total, ms[1] = loop-A kernels, ms[2] = loop-B kernels (the
+ * split is measured in a second pass when split != 0). */
+int sse_time_residual(sse_handle* h, int reps, int split, float* ms);
+int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
+int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSE_B200_H */

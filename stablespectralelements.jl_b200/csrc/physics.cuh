@@ -1,0 +1,216 @@
+// Pointwise physics as __device__ functions (FP64).
+//
+// Restates /root/reference/src/ConservationLaws/: logmean / inv_logmean
+// (ConservationLaws.jl:132-156), Euler maps and fluxes (euler_navierstokes.jl:58-225), linear
+// advection (linear_advection_diffusion.jl:53-119) and Burgers (burgers.jl:51-133).
+//
+// Two-point fluxes are evaluated already contracted with a direction vector c:
+//   out[e] = sum_n c[n] * F[e][n](u_L, u_R)
+// which is the only way the residual ever uses the flux tensor
+// (flux_differencing_form.jl:20-33,108-121; ConservationLaws.jl:92-100).
+#pragma once
+#include <math.h>
+
+namespace sse {
+
+enum { LAW_ADV = 0, LAW_BURGERS = 1, LAW_EULER = 2 };
+
+struct Phys {
+  double a[3];
+  double b;
+  double gamma;
+  double half_lambda;
+  int inviscid;    // sse_inviscid_flux
+  int two_point;   // sse_two_point_flux used by the interface flux / volume terms
+};
+
+template <int DIM, int LAW> struct LawTraits {
+  static constexpr int NC = (LAW == LAW_EULER) ? DIM + 2 : 1;
+  // per-node state kept in shared memory: Euler primitives {rho, V[DIM], p, rho/p}; scalar {u}
+  static constexpr int NS = (LAW == LAW_EULER) ? DIM + 3 : 1;
+};
+
+__device__ __forceinline__ double logmean(double x, double y) {
+  double f2 = (x * (x - 2.0 * y) + y * y) / (x * (x + 2.0 * y) + y * y);
+  if (f2 < 1.0e-4) return (x + y) * 105.0 / (210.0 + f2 * (70.0 + f2 * (42.0 + f2 * 30.0)));
+  return (y - x) / log(y / x);
+}
+
+__device__ __forceinline__ double inv_logmean(double x, double y) {
+  double f2 = (x * (x - 2.0 * y) + y * y) / (x * (x + 2.0 * y) + y * y);
+  if (f2 < 1.0e-4) return (210.0 + f2 * (70.0 + f2 * (42.0 + f2 * 30.0))) / ((x + y) * 105.0);
+  return log(y / x) / (y - x);
+}
+
+// conservative -> shared-memory state
+template <int DIM, int LAW>
+__device__ __forceinline__ void cons_to_state(const Phys& P, const double* u, double* s) {
+  if constexpr (LAW == LAW_EULER) {
+    double rho = u[0];
+    double k = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      s[1 + m] = u[1 + m] / rho;
+      k += s[1 + m] * s[1 + m];
+    }
+    double p = (P.gamma - 1.0) * (u[DIM + 1] - 0.5 * rho * k);
+    s[0] = rho;
+    s[DIM + 1] = p;
+    s[DIM + 2] = rho / p;
+  } else {
+    s[0] = u[0];
+  }
+}
+
+template <int DIM, int LAW>
+__device__ __forceinline__ void state_to_cons(const Phys& P, const double* s, double* u) {
+  if constexpr (LAW == LAW_EULER) {
+    double k = 0.0;
+    u[0] = s[0];
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      u[1 + m] = s[0] * s[1 + m];
+      k += s[1 + m] * s[1 + m];
+    }
+    u[DIM + 1] = s[DIM + 1] / (P.gamma - 1.0) + 0.5 * s[0] * k;
+  } else {
+    u[0] = s[0];
+  }
+}
+
+// physical flux contracted with c, from the state
+template <int DIM, int LAW>
+__device__ __forceinline__ void physical_flux_c(const Phys& P, const double* s, const double* c,
+                                                double* out) {
+  if constexpr (LAW == LAW_EULER) {
+    double vc = 0.0, k = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      vc += s[1 + m] * c[m];
+      k += s[1 + m] * s[1 + m];
+    }
+    double rho = s[0], p = s[DIM + 1];
+    double E = p / (P.gamma - 1.0) + 0.5 * rho * k;
+    out[0] = rho * vc;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) out[1 + m] = rho * s[1 + m] * vc + p * c[m];
+    out[DIM + 1] = (E + p) * vc;
+  } else {
+    double ac = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) ac += P.a[m] * c[m];
+    if constexpr (LAW == LAW_ADV) out[0] = ac * s[0];
+    else out[0] = 0.5 * ac * s[0] * s[0];
+  }
+}
+
+// two-point flux contracted with c
+template <int DIM, int LAW>
+__device__ __forceinline__ void two_point_flux_c(const Phys& P, int kind, const double* L,
+                                                 const double* R, const double* c, double* out) {
+  if constexpr (LAW == LAW_EULER) {
+    if (kind == 1) {  // entropy-conservative (Ranocha), euler_navierstokes.jl:171-195
+      double rho_avg = logmean(L[0], R[0]);
+      double p_avg = 0.5 * (L[DIM + 1] + R[DIM + 1]);
+      double vlvr = 0.0, vc = 0.0, vlc = 0.0, vrc = 0.0;
+      double vavg[DIM];
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) {
+        vavg[m] = 0.5 * (L[1 + m] + R[1 + m]);
+        vlvr += L[1 + m] * R[1 + m];
+        vc += vavg[m] * c[m];
+        vlc += L[1 + m] * c[m];
+        vrc += R[1 + m] * c[m];
+      }
+      double C = 0.5 * vlvr + inv_logmean(L[DIM + 2], R[DIM + 2]) / (P.gamma - 1.0);
+      double f_rho = rho_avg * vc;
+      out[0] = f_rho;
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) out[1 + m] = f_rho * vavg[m] + p_avg * c[m];
+      out[DIM + 1] = f_rho * C + 0.5 * (L[DIM + 1] * vrc + R[DIM + 1] * vlc);
+    } else {  // arithmetic mean of physical fluxes, euler_navierstokes.jl:152-158
+      double fl[DIM + 2], fr[DIM + 2];
+      physical_flux_c<DIM, LAW>(P, L, c, fl);
+      physical_flux_c<DIM, LAW>(P, R, c, fr);
+#pragma unroll
+      for (int e = 0; e < DIM + 2; ++e) out[e] = 0.5 * (fl[e] + fr[e]);
+    }
+  } else {
+    double ac = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) ac += P.a[m] * c[m];
+    if constexpr (LAW == LAW_ADV) {
+      out[0] = ac * (0.5 * (L[0] + R[0]));
+    } else {
+      if (kind == 1) out[0] = ac * ((L[0] * L[0] + L[0] * R[0] + R[0] * R[0]) / 6.0);
+      else out[0] = ac * ((L[0] * L[0] + R[0] * R[0]) * 0.25);
+    }
+  }
+}
+
+// wave speed for the Lax-Friedrichs flux (unit normal n)
+template <int DIM, int LAW>
+__device__ __forceinline__ double wave_speed(const Phys& P, const double* L, const double* R,
+                                             const double* n) {
+  if constexpr (LAW == LAW_EULER) {
+    double vnl = 0.0, vnr = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      vnl += L[1 + m] * n[m];
+      vnr += R[1 + m] * n[m];
+    }
+    double cl = sqrt(P.gamma * L[DIM + 1] / L[0]);
+    double cr = sqrt(P.gamma * R[DIM + 1] / R[0]);
+    return fmax(fabs(vnl), fabs(vnr)) + fmax(cl, cr);
+  } else {
+    double an = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) an += P.a[m] * n[m];
+    if constexpr (LAW == LAW_ADV) return fabs(an);
+    else return fmax(fabs(an * L[0]), fabs(an * R[0]));
+  }
+}
+
+// entropy variables (euler_navierstokes.jl:100-131); identity for scalar laws
+template <int DIM, int LAW>
+__device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, double* w) {
+  if constexpr (LAW == LAW_EULER) {
+    double g = P.gamma, gm1 = g - 1.0;
+    double k = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) k += u[1 + m] * u[1 + m];
+    k *= 0.5 / u[0];
+    double p = gm1 * (u[DIM + 1] - k);
+    double inv_p = 1.0 / p;
+    w[0] = (g - log(p / pow(u[0], g))) / gm1 - k * inv_p;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) w[1 + m] = u[1 + m] * inv_p;
+    w[DIM + 1] = -u[0] * inv_p;
+  } else {
+    w[0] = u[0];
+  }
+}
+
+template <int DIM, int LAW>
+__device__ __forceinline__ void entropy_to_cons(const Phys& P, const double* w_in, double* u) {
+  if constexpr (LAW == LAW_EULER) {
+    double g = P.gamma, gm1 = g - 1.0, inv_gm1 = 1.0 / gm1;
+    double w[DIM + 2];
+#pragma unroll
+    for (int e = 0; e < DIM + 2; ++e) w[e] = w_in[e] * gm1;
+    double k = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) k += w[1 + m] * w[1 + m];
+    k /= (2.0 * w[DIM + 1]);
+    double s = g - w[0] + k;
+    double rho_e = pow(gm1 / pow(-w[DIM + 1], g), inv_gm1) * exp(-s * inv_gm1);
+    u[0] = -w[DIM + 1] * rho_e;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) u[1 + m] = w[1 + m] * rho_e;
+    u[DIM + 1] = rho_e * (1.0 - k);
+  } else {
+    u[0] = w_in[0];
+  }
+}
+
+}  // namespace sse

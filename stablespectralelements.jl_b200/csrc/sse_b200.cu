@@ -1,0 +1,700 @@
+// libsse_b200.so -- C ABI (include/sse_b200.h) over the sm_100a residual kernels.
+//
+// Host side of the library: packs the reference-element operators and geometric factors into
+// device-resident buffers once (north-star part (d)), derives the operator bundles the
+// reference builds in Solvers/operators.jl (S, C = R^T B, transposes), and launches the
+// element kernels of kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sse_b200.h"
+#include "kernels.cuh"
+
+using namespace sse;
+
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess)                                                            \
+      return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
+                  cudaGetErrorString(e_));                                            \
+  } while (0)
+
+struct sse_handle {
+  sse_config cfg{};
+  Tables T{};
+  Geo G{};
+  Phys P{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+  // state / scratch
+  double *u = nullptr, *dudt = nullptr, *rk_k = nullptr;
+  double *u_q = nullptr, *u_f = nullptr, *q_q = nullptr, *q_f = nullptr;
+  int64_t n_state = 0, halo_elems = 0;
+  // halo
+  int* send_off = nullptr;
+  double *send_buf = nullptr, *recv_buf = nullptr;
+  int64_t n_send = 0;
+  // launch configuration
+  int second_order = 0, proj = 0, law_t = 0;
+  int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
+  size_t smem_a = 0, smem_b = 0;
+};
+
+template <typename Tp>
+static int dev_upload(sse_handle* h, const Tp* src, size_t n, Tp** out) {
+  *out = nullptr;
+  if (n == 0) return 0;
+  void* p = nullptr;
+  CU(cudaMalloc(&p, n * sizeof(Tp)));
+  h->allocs.push_back(p);
+  h->bytes += (int64_t)(n * sizeof(Tp));
+  if (src) CU(cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  else CU(cudaMemset(p, 0, n * sizeof(Tp)));
+  *out = (Tp*)p;
+  return 0;
+}
+
+template <typename Tp>
+static int dev_upload_vec(sse_handle* h, const std::vector<Tp>& v, const Tp** out) {
+  Tp* p = nullptr;
+  // keep at least one element so table pointers are never NULL
+  if (v.empty()) {
+    Tp z{};
+    int rc = dev_upload(h, &z, 1, &p);
+    *out = p;
+    return rc;
+  }
+  int rc = dev_upload(h, v.data(), v.size(), &p);
+  *out = p;
+  return rc;
+}
+
+struct Csr {
+  std::vector<int> rp, ci;
+  std::vector<double> v;
+};
+
+static Csr csr_from(const int32_t* rp, const int32_t* ci, const double* v, int rows) {
+  Csr c;
+  c.rp.assign(rp, rp + rows + 1);
+  c.ci.assign(ci, ci + rp[rows]);
+  c.v.assign(v, v + rp[rows]);
+  return c;
+}
+
+static Csr csr_transpose(const Csr& a, int rows, int cols) {
+  Csr t;
+  t.rp.assign(cols + 1, 0);
+  for (int c : a.ci) t.rp[c + 1]++;
+  for (int i = 0; i < cols; ++i) t.rp[i + 1] += t.rp[i];
+  t.ci.resize(a.ci.size());
+  t.v.resize(a.v.size());
+  std::vector<int> pos(t.rp.begin(), t.rp.end() - 1);
+  for (int r = 0; r < rows; ++r)
+    for (int e = a.rp[r]; e < a.rp[r + 1]; ++e) {
+      int q = pos[a.ci[e]]++;
+      t.ci[q] = r;
+      t.v[q] = a.v[e];
+    }
+  return t;
+}
+
+static std::vector<double> csr_dense(const Csr& a, int rows, int cols) {
+  std::vector<double> d((size_t)rows * cols, 0.0);
+  for (int r = 0; r < rows; ++r)
+    for (int e = a.rp[r]; e < a.rp[r + 1]; ++e) d[(size_t)r * cols + a.ci[e]] += a.v[e];
+  return d;
+}
+
+// --------------------------------------------------------------------------- dispatch
+template <int DIM, int LAW>
+static int launch_a(sse_handle* h, const double* u_dev) {
+  CU(cudaFuncSetAttribute(k_nodal_values<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)h->smem_a));
+  int grid = (int)((h->cfg.N_e + h->E_a - 1) / h->E_a);
+  k_nodal_values<DIM, LAW><<<grid, h->thr_a, h->smem_a, h->stream>>>(h->T, h->G, h->P, u_dev,
+                                                                     h->u_q, h->u_f, h->E_a,
+                                                                     h->proj);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int DIM, int LAW>
+static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
+  int grid = (int)((h->cfg.N_e + h->E_b - 1) / h->E_b);
+  if (h->cfg.strategy == SSE_PHYSICAL_OPERATOR) {
+    CU(cudaFuncSetAttribute(k_physical<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)h->smem_b));
+    if (h->second_order) {
+      RK none{};
+      k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+          h->T, h->G, h->P, none, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 0, 1);
+      h->launches++;
+    }
+    k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+        h->T, h->G, h->P, rk, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 1,
+        h->second_order);
+  } else if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
+    CU(cudaFuncSetAttribute(k_fluxdiff<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)h->smem_b));
+    k_fluxdiff<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(h->T, h->G, h->P, rk, h->u_q,
+                                                                   h->u_f, dudt_dev, h->E_b);
+  } else {
+    CU(cudaFuncSetAttribute(k_standard_ref<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)h->smem_b));
+    k_standard_ref<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+        h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->E_b);
+  }
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+#define SSE_DISPATCH(fn, ...)                                                        \
+  switch (h->cfg.dim * 10 + h->law_t) {                                              \
+    case 10: return fn<1, LAW_ADV>(__VA_ARGS__);                                     \
+    case 11: return fn<1, LAW_BURGERS>(__VA_ARGS__);                                 \
+    case 12: return fn<1, LAW_EULER>(__VA_ARGS__);                                   \
+    case 20: return fn<2, LAW_ADV>(__VA_ARGS__);                                     \
+    case 21: return fn<2, LAW_BURGERS>(__VA_ARGS__);                                 \
+    case 22: return fn<2, LAW_EULER>(__VA_ARGS__);                                   \
+    case 30: return fn<3, LAW_ADV>(__VA_ARGS__);                                     \
+    case 31: return fn<3, LAW_BURGERS>(__VA_ARGS__);                                 \
+    case 32: return fn<3, LAW_EULER>(__VA_ARGS__);                                   \
+    default: return fail("unsupported dim/law combination");                         \
+  }
+
+static int run_a(sse_handle* h, const double* u_dev) { SSE_DISPATCH(launch_a, h, u_dev); }
+static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
+  SSE_DISPATCH(launch_b, h, dudt_dev, rk);
+}
+
+// ------------------------------------------------------------------------------- API
+extern "C" {
+
+const char* sse_last_error(void) { return g_err.c_str(); }
+int sse_version(void) { return 100; }
+
+int sse_destroy(sse_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators* ops,
+                       const sse_geometry* geo, const int64_t* mapP) {
+  const int d = cfg->dim, Np = cfg->N_p, Nq = cfg->N_q, Nf = cfg->N_f, Nc = cfg->N_c;
+  const int64_t Ne = cfg->N_e;
+  if (d < 1 || d > 3) return fail("dim must be 1, 2 or 3");
+  if (Ne < 1 || Np < 1 || Nq < 1 || Nf < 1) return fail("empty discretization");
+  if (cfg->num_faces < 1 || Nf % cfg->num_faces) return fail("N_f must be a multiple of num_faces");
+  int law_t;
+  h->second_order = 0;
+  switch (cfg->law) {
+    case SSE_LAW_ADVECTION: law_t = LAW_ADV; break;
+    case SSE_LAW_BURGERS: law_t = LAW_BURGERS; break;
+    case SSE_LAW_EULER: law_t = LAW_EULER; break;
+    case SSE_LAW_ADVECTION_DIFFUSION: law_t = LAW_ADV; h->second_order = 1; break;
+    case SSE_LAW_VISCOUS_BURGERS: law_t = LAW_BURGERS; h->second_order = 1; break;
+    default: return fail("unknown conservation law %d", cfg->law);
+  }
+  h->law_t = law_t;
+  const int nc_expected = (law_t == LAW_EULER) ? d + 2 : 1;
+  if (Nc != nc_expected) return fail("N_c = %d does not match the conservation law (%d)", Nc, nc_expected);
+  if (h->second_order && (cfg->strategy != SSE_PHYSICAL_OPERATOR || cfg->form != SSE_FORM_STANDARD))
+    return fail("second-order equations need StandardForm with PhysicalOperators");
+  if (cfg->form == SSE_FORM_FLUX_DIFFERENCING && cfg->strategy == SSE_PHYSICAL_OPERATOR)
+    return fail("no physical-operator formulation for the flux-differencing form");
+  if ((int64_t)Nf * (Ne + (cfg->N_halo + Nf - 1) / Nf) * Nc >= (1LL << 31))
+    return fail("trace array too large for 32-bit offsets");
+  if (!ops->R_rowptr || !ops->W || !ops->B || !geo->J_q || !geo->Lambda_q || !geo->J_f ||
+      !geo->nJf || !mapP)
+    return fail("missing operator/geometry arrays");
+
+  CU(cudaSetDevice(cfg->device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+
+  Tables& T = h->T;
+  T.dim = d; T.N_p = Np; T.N_q = Nq; T.N_f = Nf; T.N_c = Nc;
+  T.nfaces = cfg->num_faces; T.npf = Nf / cfg->num_faces; T.n1 = ops->n1d;
+  T.v_kind = cfg->v_kind; T.mass_kind = cfg->mass_solver; T.r_is_selection = cfg->r_is_selection;
+  T.has_Minv = ops->Minv != nullptr;
+
+  // ---- V
+  if (cfg->v_kind == SSE_V_DENSE) {
+    if (!ops->V_dense) return fail("V_dense missing");
+    std::vector<double> Vt((size_t)Np * Nq);
+    for (int i = 0; i < Nq; ++i)
+      for (int p = 0; p < Np; ++p) Vt[(size_t)p * Nq + i] = ops->V_dense[(size_t)i * Np + p];
+    double* p1; double* p2;
+    if (dev_upload(h, ops->V_dense, (size_t)Nq * Np, &p1)) return -1;
+    if (dev_upload(h, Vt.data(), Vt.size(), &p2)) return -1;
+    T.Vd = p1; T.VdT = p2;
+  } else if (cfg->v_kind == SSE_V_WARPED) {
+    int n = ops->n1d;
+    if (d < 2 || n < 1 || !ops->warp_A || !ops->warp_B || !ops->sigma_i || (d == 3 && !ops->warp_C))
+      return fail("warped-product tables missing");
+    size_t nd = 1;
+    for (int m = 0; m < d; ++m) nd *= n;
+    if ((int)nd != Nq) return fail("warped product needs N_q = n1d^dim");
+    // the kernels assume the simplex index pattern N2[b1] = n-b1, N3[b1,b2] = n-b1-b2
+    for (int b1 = 0; b1 < n; ++b1)
+      for (int b2 = 0; b2 < n; ++b2) {
+        if (d == 2) {
+          bool used = ops->sigma_i[b1 * n + b2] >= 0;
+          if (used != (b2 < n - b1)) return fail("sigma_i is not a simplex pattern");
+        } else {
+          for (int b3 = 0; b3 < n; ++b3) {
+            bool used = ops->sigma_i[(b1 * n + b2) * n + b3] >= 0;
+            if (used != (b2 < n - b1 && b3 < n - b1 - b2)) return fail("sigma_i is not a simplex pattern");
+          }
+        }
+      }
+    double *pA, *pB, *pC = nullptr; int* ps;
+    if (dev_upload(h, ops->warp_A, (size_t)n * n, &pA)) return -1;
+    if (dev_upload(h, ops->warp_B, (size_t)n * n * n, &pB)) return -1;
+    if (d == 3 && dev_upload(h, ops->warp_C, (size_t)n * n * n * n, &pC)) return -1;
+    if (dev_upload(h, ops->sigma_i, nd, &ps)) return -1;
+    T.wA = pA; T.wB = pB; T.wC = pC; T.sig = ps;
+  } else if (cfg->v_kind == SSE_V_IDENTITY) {
+    if (Np != Nq) return fail("identity V needs N_p = N_q");
+  } else {
+    return fail("unknown v_kind");
+  }
+  if (cfg->mass_solver == SSE_MASS_DIAGONAL && cfg->v_kind != SSE_V_IDENTITY)
+    return fail("diagonal mass solver needs a nodal scheme");
+  if (T.n1 < 1) T.n1 = 1;
+
+  // ---- sparse reference operators
+  Csr R = csr_from(ops->R_rowptr, ops->R_col, ops->R_val, Nf);
+  Csr Rt = csr_transpose(R, Nf, Nq);
+  std::vector<double> Cv(Rt.v.size());
+  for (int i = 0; i < Nq; ++i)
+    for (int e = Rt.rp[i]; e < Rt.rp[i + 1]; ++e) Cv[e] = Rt.v[e] * ops->B[Rt.ci[e]];
+  std::vector<int> Rslot(R.ci.size());
+  for (int j = 0; j < Nf; ++j)
+    for (int e = R.rp[j]; e < R.rp[j + 1]; ++e) {
+      int i = R.ci[e], slot = -1;
+      for (int q = Rt.rp[i]; q < Rt.rp[i + 1]; ++q)
+        if (Rt.ci[q] == j) { slot = q; break; }
+      Rslot[e] = slot;
+    }
+  T.nnzRt = (int)Rt.ci.size();
+  if (dev_upload_vec(h, R.rp, &T.R_rp) || dev_upload_vec(h, R.ci, &T.R_ci) ||
+      dev_upload_vec(h, R.v, &T.R_v) || dev_upload_vec(h, Rslot, &T.R_slot) ||
+      dev_upload_vec(h, Rt.rp, &T.Rt_rp) || dev_upload_vec(h, Rt.ci, &T.Rt_ci) ||
+      dev_upload_vec(h, Rt.v, &T.Rt_v) || dev_upload_vec(h, Cv, &T.C_v))
+    return -1;
+
+  std::vector<double> Gref;
+  if (ops->Lambda_ref) {
+    if (!ops->J_ref) return fail("J_ref missing");
+    Gref.resize((size_t)Nq * d * d);
+    for (int i = 0; i < Nq; ++i)
+      for (int q = 0; q < d * d; ++q)
+        Gref[(size_t)i * d * d + q] = ops->Lambda_ref[(size_t)i * d * d + q] / ops->J_ref[i];
+    if (dev_upload_vec(h, Gref, &T.Gref)) return -1;
+  }
+  const bool need_D = cfg->strategy == SSE_REFERENCE_OPERATOR;
+  if (need_D) {
+    std::vector<std::vector<double>> Dd(d);
+    for (int m = 0; m < d; ++m) {
+      if (!ops->D_rowptr[m]) return fail("D operators missing");
+      Csr D = csr_from(ops->D_rowptr[m], ops->D_col[m], ops->D_val[m], Nq);
+      Csr Dt = csr_transpose(D, Nq, Nq);
+      if (dev_upload_vec(h, D.rp, &T.D_rp[m]) || dev_upload_vec(h, D.ci, &T.D_ci[m]) ||
+          dev_upload_vec(h, D.v, &T.D_v[m]) || dev_upload_vec(h, Dt.rp, &T.Dt_rp[m]) ||
+          dev_upload_vec(h, Dt.ci, &T.Dt_ci[m]) || dev_upload_vec(h, Dt.v, &T.Dt_v[m]))
+        return -1;
+      Dd[m] = csr_dense(D, Nq, Nq);
+    }
+    if (cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
+      // S_m = ½ (W D_ξm − D_ξm^T W),  D_ξm = Σ_l diag(Λ_ref[:,l,m]/J_ref) D_ηl
+      // (operators.jl:186-204, SpatialDiscretizations.jl:414-419)
+      std::vector<std::vector<double>> S(d, std::vector<double>((size_t)Nq * Nq, 0.0));
+      for (int m = 0; m < d; ++m) {
+        std::vector<double> Dxi((size_t)Nq * Nq, 0.0);
+        for (int i = 0; i < Nq; ++i)
+          for (int j = 0; j < Nq; ++j) {
+            double v = 0.0;
+            if (Gref.empty()) v = Dd[m][(size_t)i * Nq + j];
+            else
+              for (int l = 0; l < d; ++l)
+                v += Gref[((size_t)i * d + l) * d + m] * Dd[l][(size_t)i * Nq + j];
+            Dxi[(size_t)i * Nq + j] = v;
+          }
+        for (int i = 0; i < Nq; ++i)
+          for (int j = 0; j < Nq; ++j)
+            S[m][(size_t)i * Nq + j] = 0.5 * (ops->W[i] * Dxi[(size_t)i * Nq + j] -
+                                              Dxi[(size_t)j * Nq + i] * ops->W[j]);
+      }
+      Csr A;
+      A.rp.assign(Nq + 1, 0);
+      for (int i = 0; i < Nq; ++i) {
+        for (int j = 0; j < Nq; ++j) {
+          if (i == j) continue;
+          bool nz = false;
+          for (int m = 0; m < d; ++m)
+            nz = nz || S[m][(size_t)i * Nq + j] != 0.0 || S[m][(size_t)j * Nq + i] != 0.0;
+          if (nz) {
+            A.ci.push_back(j);
+            for (int m = 0; m < d; ++m) A.v.push_back(S[m][(size_t)i * Nq + j]);
+          }
+        }
+        A.rp[i + 1] = (int)A.ci.size();
+      }
+      if (dev_upload_vec(h, A.rp, &T.S_rp) || dev_upload_vec(h, A.ci, &T.S_ci) ||
+          dev_upload_vec(h, A.v, &T.S_v))
+        return -1;
+    }
+  }
+  {
+    double *pW, *pB, *pn;
+    if (dev_upload(h, ops->W, Nq, &pW) || dev_upload(h, ops->B, Nf, &pB)) return -1;
+    T.W = pW; T.B = pB;
+    if (!ops->n_ref) return fail("n_ref missing");
+    if (dev_upload(h, ops->n_ref, (size_t)cfg->num_faces * d, &pn)) return -1;
+    T.n_ref = pn;
+    if (ops->Minv) {
+      double* pm;
+      if (dev_upload(h, ops->Minv, (size_t)Np * Np, &pm)) return -1;
+      T.Minv = pm;
+    }
+  }
+
+  // ---- geometry (kept in the reference's layout: every element block is contiguous)
+  Geo& G = h->G;
+  G.N_e = Ne;
+  {
+    double *p1, *p2, *p3, *p4;
+    if (dev_upload(h, geo->J_q, (size_t)Nq * Ne, &p1) ||
+        dev_upload(h, geo->Lambda_q, (size_t)Nq * d * d * Ne, &p2) ||
+        dev_upload(h, geo->J_f, (size_t)Nf * Ne, &p3) ||
+        dev_upload(h, geo->nJf, (size_t)d * Nf * Ne, &p4))
+      return -1;
+    G.J_q = p1; G.L_q = p2; G.J_f = p3; G.nJf = p4;
+  }
+  if (cfg->strategy == SSE_PHYSICAL_OPERATOR) {
+    if (!geo->VOL || !geo->FAC) return fail("VOL/FAC missing for PhysicalOperator");
+    double *p1, *p2;
+    if (dev_upload(h, geo->VOL, (size_t)Nq * Np * d * Ne, &p1) ||
+        dev_upload(h, geo->FAC, (size_t)Nf * Np * Ne, &p2))
+      return -1;
+    G.VOL = p1; G.FAC = p2;
+  }
+  if (cfg->mass_solver == SSE_MASS_CHOLESKY && cfg->strategy != SSE_PHYSICAL_OPERATOR) {
+    if (!geo->Minv_elem) return fail("Minv_elem missing for the Cholesky mass solver");
+    double* p1;
+    if (dev_upload(h, geo->Minv_elem, (size_t)Np * Np * Ne, &p1)) return -1;
+    G.Minv_e = p1;
+  }
+  {
+    h->halo_elems = (cfg->N_halo + Nf - 1) / Nf;
+    const int64_t ntr = (int64_t)Nf * (Ne + h->halo_elems);
+    std::vector<int> toff((size_t)Nf * Ne), mp((size_t)Nf * Ne);
+    for (int64_t g = 0; g < (int64_t)Nf * Ne; ++g) {
+      int64_t t = mapP[g];
+      if (t < 0 || t >= ntr) return fail("mapP[%lld] = %lld out of range", (long long)g, (long long)t);
+      int64_t kp = t / Nf, jp = t % Nf;
+      toff[g] = (int)(kp * Nc * Nf + jp);
+      mp[g] = (int)t;
+    }
+    int *p1, *p2;
+    if (dev_upload(h, toff.data(), toff.size(), &p1) || dev_upload(h, mp.data(), mp.size(), &p2))
+      return -1;
+    G.toff = p1; G.mapP = p2;
+  }
+
+  // ---- physics
+  Phys& P = h->P;
+  for (int m = 0; m < 3; ++m) P.a[m] = cfg->a[m];
+  P.b = cfg->b; P.gamma = cfg->gamma; P.half_lambda = cfg->half_lambda;
+  P.inviscid = cfg->inviscid_flux;
+  P.two_point = (cfg->form == SSE_FORM_FLUX_DIFFERENCING) ? cfg->two_point_flux : 0;
+
+  // ---- state / scratch
+  h->n_state = (int64_t)Np * Nc * Ne;
+  if (dev_upload<double>(h, nullptr, h->n_state, &h->u) ||
+      dev_upload<double>(h, nullptr, h->n_state, &h->dudt) ||
+      dev_upload<double>(h, nullptr, h->n_state, &h->rk_k) ||
+      dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->u_q) ||
+      dev_upload<double>(h, nullptr, (size_t)Nf * Nc * (Ne + h->halo_elems), &h->u_f))
+    return -1;
+  if (h->second_order) {
+    if (cfg->N_halo) return fail("halo exchange is not implemented for second-order equations");
+    if (dev_upload<double>(h, nullptr, (size_t)Nq * Nc * d * Ne, &h->q_q) ||
+        dev_upload<double>(h, nullptr, (size_t)Nf * Nc * d * Ne, &h->q_f))
+      return -1;
+  }
+  if (cfg->N_halo) {
+    if (dev_upload<double>(h, nullptr, (size_t)cfg->N_halo * Nc, &h->recv_buf)) return -1;
+  }
+
+  // ---- projection mode of loop A (flux_differencing_form.jl:171-292)
+  h->proj = 0;
+  if (cfg->form == SSE_FORM_FLUX_DIFFERENCING && Nc > 1) {
+    if (cfg->v_kind == SSE_V_IDENTITY) h->proj = cfg->r_is_selection ? 0 : 1;
+    else h->proj = 2;
+  }
+
+  // ---- launch configuration: E elements per CTA, shared memory per kernel
+  int dev_smem = 0;
+  CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+  const size_t budget = (size_t)std::min(dev_smem, 200 * 1024);
+  size_t nd = 1;
+  for (int m = 0; m < d; ++m) nd *= T.n1;
+  const size_t wtmp = (cfg->v_kind == SSE_V_WARPED) ? 2 * nd : 0;   // per (element, component)
+  const int NS = (law_t == LAW_EULER) ? d + 3 : 1;
+  auto smem_a = [&](int E) {
+    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf + wtmp * Nc);
+  };
+  auto smem_b = [&](int E) -> size_t {
+    if (cfg->strategy == SSE_PHYSICAL_OPERATOR)
+      return sizeof(double) * (size_t)E * d * Nc * ((size_t)2 * Nq + Nf + Np + wtmp);
+    if (cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
+      size_t sD = std::max((size_t)T.nnzRt * Nc, wtmp * Nc);
+      return sizeof(double) * (size_t)E * ((size_t)NS * Nq + (size_t)d * d * Nq + (size_t)NS * Nf +
+                                           (size_t)Nc * Nf + (size_t)Nf * d + (size_t)Nc * Nq +
+                                           (size_t)Nc * Np + sD);
+    }
+    return sizeof(double) * (size_t)E * ((size_t)d * d * Nq + 2 * (size_t)d * Nc * Nq + (size_t)Nc * Nf +
+                                         (size_t)Nc * Nq + (size_t)Nc * Np + wtmp * Nc);
+  };
+  auto pick = [&](auto fn, int* E, int* thr, size_t* sm) -> int {
+    int e = std::max(1, std::min(32, 128 / Nq));
+    e = (int)std::min<int64_t>(e, Ne);
+    while (e > 1 && fn(e) > budget) --e;
+    if (fn(e) > budget) return fail("element does not fit in shared memory (%zu B)", fn(e));
+    *E = e; *sm = fn(e);
+    int t = ((e * Nq + 31) / 32) * 32;
+    *thr = std::max(64, std::min(256, t));
+    return 0;
+  };
+  if (pick(smem_a, &h->E_a, &h->thr_a, &h->smem_a)) return -1;
+  if (pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b)) return -1;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sse_create(const sse_config* cfg, const sse_operators* ops, const sse_geometry* geo,
+               const int64_t* mapP, sse_handle** out) {
+  if (!cfg || !ops || !geo || !out) return fail("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available (libsse_b200 has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("invalid device ordinal %d", cfg->device);
+  sse_handle* h = new sse_handle();
+  h->cfg = *cfg;
+  if (create_impl(h, cfg, ops, geo, mapP)) {
+    std::string keep = g_err;
+    sse_destroy(h);
+    g_err = keep;
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+int sse_nodal_values(sse_handle* h, const double* u_dev) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  return run_a(h, u_dev ? u_dev : h->u);
+}
+
+int sse_time_derivative(sse_handle* h, double* dudt_dev) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  RK rk{};
+  return run_b(h, dudt_dev ? dudt_dev : h->dudt, rk);
+}
+
+int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int where) {
+  (void)t;  // the reference's residual ignores t as well (no source terms are applied)
+  if (!h || !u || !dudt) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  RK rk{};
+  if (where == SSE_DEVICE) {
+    if (run_a(h, u)) return -1;
+    return run_b(h, dudt, rk);
+  }
+  CU(cudaMemcpyAsync(h->u, u, h->n_state * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (run_a(h, h->u)) return -1;
+  if (run_b(h, h->dudt, rk)) return -1;
+  CU(cudaMemcpyAsync(dudt, h->dudt, h->n_state * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sse_set_state(sse_handle* h, const double* u_host) {
+  if (!h || !u_host) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->u, u_host, h->n_state * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->rk_k, 0, h->n_state * sizeof(double), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sse_get_state(sse_handle* h, double* u_host) {
+  if (!h || !u_host) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(u_host, h->u, h->n_state * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sse_state_ptr(sse_handle* h, double** u_dev, double** dudt_dev) {
+  if (!h) return fail("null handle");
+  if (u_dev) *u_dev = h->u;
+  if (dudt_dev) *dudt_dev = h->dudt;
+  return 0;
+}
+
+int sse_rk_stage(sse_handle* h, double a, double b, double dt) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  RK rk{1, a, b, dt, h->rk_k, h->u};
+  if (run_a(h, h->u)) return -1;
+  return run_b(h, h->dudt, rk);
+}
+
+int sse_rk_step_ck54(sse_handle* h, double dt) {
+  static const double A[5] = {0.0, -567301805773.0 / 1357537059087.0,
+                              -2404267990393.0 / 2016746695238.0,
+                              -3550918686646.0 / 2091501179385.0,
+                              -1275806237668.0 / 842570457699.0};
+  static const double B[5] = {1432997174477.0 / 9575080441755.0,
+                              5161836677717.0 / 13612068292357.0,
+                              1720146321549.0 / 2090206949498.0,
+                              3134564353537.0 / 4481467310338.0,
+                              2277821191437.0 / 14882151754819.0};
+  for (int s = 0; s < 5; ++s)
+    if (sse_rk_stage(h, A[s], B[s], dt)) return -1;
+  return 0;
+}
+
+int sse_halo_setup(sse_handle* h, const int64_t* send_idx, int64_t n_send) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  const int Nf = h->cfg.N_f, Nc = h->cfg.N_c;
+  std::vector<int> off((size_t)n_send);
+  for (int64_t s = 0; s < n_send; ++s) {
+    int64_t g = send_idx[s];
+    if (g < 0 || g >= (int64_t)Nf * h->cfg.N_e) return fail("send index out of range");
+    off[s] = (int)((g / Nf) * Nc * Nf + g % Nf);
+  }
+  if (dev_upload(h, off.data(), off.size(), &h->send_off)) return -1;
+  if (dev_upload<double>(h, nullptr, (size_t)n_send * Nc, &h->send_buf)) return -1;
+  h->n_send = n_send;
+  return 0;
+}
+
+int sse_halo_buffers(sse_handle* h, double** send_dev, double** recv_dev, int64_t* n_send,
+                     int64_t* n_recv) {
+  if (!h) return fail("null handle");
+  if (send_dev) *send_dev = h->send_buf;
+  if (recv_dev) *recv_dev = h->recv_buf;
+  if (n_send) *n_send = h->n_send;
+  if (n_recv) *n_recv = h->cfg.N_halo;
+  return 0;
+}
+
+int sse_halo_pack(sse_handle* h) {
+  if (!h) return fail("null handle");
+  if (h->n_send == 0) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  int n = (int)h->n_send;
+  k_halo_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(h->u_f, h->send_off, n, h->cfg.N_c,
+                                                      h->cfg.N_f, h->send_buf);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sse_halo_unpack(sse_handle* h) {
+  if (!h) return fail("null handle");
+  if (h->cfg.N_halo == 0) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  int n = (int)h->cfg.N_halo;
+  k_halo_unpack<<<(n + 255) / 256, 256, 0, h->stream>>>(h->u_f, h->recv_buf, n, h->cfg.N_c,
+                                                        h->cfg.N_f, h->cfg.N_e);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sse_sync(sse_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void* sse_stream(sse_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int sse_time_residual(sse_handle* h, int reps, int split, float* ms) {
+  if (!h || !ms || reps < 1) return fail("bad argument");
+  CU(cudaSetDevice(h->cfg.device));
+  RK rk{};
+  ms[0] = ms[1] = ms[2] = 0.f;
+  CU(cudaEventRecord(h->ev[0], h->stream));
+  for (int r = 0; r < reps; ++r) {
+    if (run_a(h, h->u)) return -1;
+    if (run_b(h, h->dudt, rk)) return -1;
+  }
+  CU(cudaEventRecord(h->ev[1], h->stream));
+  CU(cudaEventSynchronize(h->ev[1]));
+  CU(cudaEventElapsedTime(&ms[0], h->ev[0], h->ev[1]));
+  if (split) {
+    for (int r = 0; r < reps; ++r) {
+      float ta = 0.f, tb = 0.f;
+      CU(cudaEventRecord(h->ev[0], h->stream));
+      if (run_a(h, h->u)) return -1;
+      CU(cudaEventRecord(h->ev[1], h->stream));
+      if (run_b(h, h->dudt, rk)) return -1;
+      CU(cudaEventRecord(h->ev[2], h->stream));
+      CU(cudaEventSynchronize(h->ev[2]));
+      CU(cudaEventElapsedTime(&ta, h->ev[0], h->ev[1]));
+      CU(cudaEventElapsedTime(&tb, h->ev[1], h->ev[2]));
+      ms[1] += ta;
+      ms[2] += tb;
+    }
+  }
+  return 0;
+}
+
+int64_t sse_kernel_launches(sse_handle* h) { return h ? h->launches : 0; }
+int64_t sse_device_bytes(sse_handle* h) { return h ? h->bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+"""ctypes binding of ``libsse_b200.so`` (include/sse_b200.h) and the packer that turns a host
+``Solver`` into the ``sse_config`` / ``sse_operators`` / ``sse_geometry`` structs.
+
+This is the Python counterpart of the Julia ``ccall`` shim shown in INTEGRATION.md.  The
+library must be present (built by ``__graft_entry__.build()``); there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .linear_maps import (IdentityMap, SelectionMap, WarpedTensorProductMap2D,
+                          WarpedTensorProductMap3D)
+from .reference_approximation import NoMapping
+
+_LIB = None
+LIB_NAME = "libsse_b200.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+LAW = dict(advection=0, burgers=1, euler=2, advection_diffusion=3, viscous_burgers=4)
+INVISCID = dict(lf=0, central=1, ec=2)
+MASS = dict(diagonal=0, weight_adjusted=1, cholesky=2)
+
+c_d_p = C.POINTER(C.c_double)
+c_i32_p = C.POINTER(C.c_int32)
+c_i64_p = C.POINTER(C.c_int64)
+
+
+class SseConfig(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("N_p", C.c_int32), ("N_q", C.c_int32), ("N_f", C.c_int32),
+                ("N_c", C.c_int32), ("num_faces", C.c_int32), ("N_e", C.c_int64),
+                ("N_halo", C.c_int64), ("law", C.c_int32), ("a", C.c_double * 3),
+                ("b", C.c_double), ("gamma", C.c_double), ("form", C.c_int32),
+                ("strategy", C.c_int32), ("inviscid_flux", C.c_int32),
+                ("half_lambda", C.c_double), ("two_point_flux", C.c_int32),
+                ("v_kind", C.c_int32), ("r_is_selection", C.c_int32),
+                ("mass_solver", C.c_int32), ("device", C.c_int32)]
+
+
+class SseOperators(C.Structure):
+    _fields_ = [("V_dense", c_d_p), ("n1d", C.c_int32), ("warp_A", c_d_p), ("warp_B", c_d_p),
+                ("warp_C", c_d_p), ("sigma_i", c_i32_p),
+                ("R_rowptr", c_i32_p), ("R_col", c_i32_p), ("R_val", c_d_p),
+                ("D_rowptr", c_i32_p * 3), ("D_col", c_i32_p * 3), ("D_val", c_d_p * 3),
+                ("W", c_d_p), ("B", c_d_p), ("Lambda_ref", c_d_p), ("J_ref", c_d_p),
+                ("n_ref", c_d_p), ("Minv", c_d_p)]
+
+
+class SseGeometry(C.Structure):
+    _fields_ = [("J_q", c_d_p), ("Lambda_q", c_d_p), ("J_f", c_d_p), ("nJf", c_d_p),
+                ("VOL", c_d_p), ("FAC", c_d_p), ("Minv_elem", c_d_p)]
+
+
+EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_residual",
+           "sse_nodal_values", "sse_time_derivative", "sse_set_state", "sse_get_state",
+           "sse_state_ptr", "sse_rk_stage", "sse_rk_step_ck54", "sse_halo_setup",
+           "sse_halo_buffers", "sse_halo_pack", "sse_halo_unpack", "sse_sync", "sse_stream",
+           "sse_time_residual", "sse_kernel_launches", "sse_device_bytes"]
+
+
+def load_library(path: Optional[str] = None):
+    """Load libsse_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} not found: run `python -c 'import __graft_entry__ as g; "
+                           f"g.build()'` first -- the residual has no CPU fallback")
+    lib = C.CDLL(p)
+    vp = C.c_void_p
+    lib.sse_last_error.restype = C.c_char_p
+    lib.sse_version.restype = C.c_int
+    lib.sse_create.argtypes = [C.POINTER(SseConfig), C.POINTER(SseOperators),
+                               C.POINTER(SseGeometry), c_i64_p, C.POINTER(vp)]
+    lib.sse_destroy.argtypes = [vp]
+    lib.sse_residual.argtypes = [vp, vp, vp, C.c_double, C.c_int]
+    lib.sse_nodal_values.argtypes = [vp, vp]
+    lib.sse_time_derivative.argtypes = [vp, vp]
+    lib.sse_set_state.argtypes = [vp, vp]
+    lib.sse_get_state.argtypes = [vp, vp]
+    lib.sse_state_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.sse_rk_stage.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.sse_rk_step_ck54.argtypes = [vp, C.c_double]
+    lib.sse_halo_setup.argtypes = [vp, c_i64_p, C.c_int64]
+    lib.sse_halo_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), c_i64_p, c_i64_p]
+    lib.sse_halo_pack.argtypes = [vp]
+    lib.sse_halo_unpack.argtypes = [vp]
+    lib.sse_sync.argtypes = [vp]
+    lib.sse_stream.argtypes = [vp]
+    lib.sse_stream.restype = vp
+    lib.sse_time_residual.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    lib.sse_kernel_launches.argtypes = [vp]
+    lib.sse_kernel_launches.restype = C.c_int64
+    lib.sse_device_bytes.argtypes = [vp]
+    lib.sse_device_bytes.restype = C.c_int64
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_d_p) if a is not None else c_d_p()
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_i32_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def physical_operators(solver):
+    """Per-element dense VOL/FAC (Solvers/operators.jl:85-164), built once on the host.
+
+    Returns VOL (N_e, d, N_p, N_q) and FAC (N_e, N_p, N_f), C-contiguous."""
+    sd = solver.spatial_discretization
+    ra = sd.reference_approximation
+    gf = sd.geometric_factors
+    d, N_e = ra.dim, sd.N_e
+    V, R = ra.V.to_dense(), ra.R.to_dense()
+    D = [Dm.to_dense() for Dm in ra.D]
+    W, B = ra.W, ra.B
+    skew = solver.form_desc["mapping_form"] == "skew"
+    from .geometric_factors import apply_reference_mapping
+    Lq = apply_reference_mapping(gf, ra.reference_mapping)       # (N_e, n, m, N_q)
+    J = gf.J_q
+    if solver.mass_kind == "diagonal":
+        Minv = np.zeros((N_e, ra.N_p, ra.N_p))
+        idx = np.arange(ra.N_p)
+        Minv[:, idx, idx] = 1.0 / (W[None, :] * J)
+    elif solver.mass_kind == "cholesky":
+        Minv = np.linalg.inv(np.einsum("qa,kq,qb->kab", V, W[None, :] * J, V))
+    else:
+        Minv = np.einsum("qa,kq,qb->kab", V, W[None, :] / J, V)
+        if solver.Minv is not None:
+            Minv = solver.Minv[None] @ Minv @ solver.Minv[None]
+    VOL = np.empty((N_e, d, ra.N_p, ra.N_q))
+    for n in range(d):
+        if d == 1 and not skew:
+            A = np.broadcast_to(D[0].T * W[None, :], (N_e,) + D[0].shape)
+        elif not skew:
+            A = sum(D[m].T[None] * (W[None, :] * Lq[:, n, m, :])[:, None, :] for m in range(d))
+        else:
+            A = sum(D[m].T[None] * (0.5 * W[None, :] * Lq[:, n, m, :])[:, None, :]
+                    - (0.5 * W[None, :] * Lq[:, n, m, :])[:, :, None] * D[m][None]
+                    for m in range(d))
+            A = A + np.einsum("fq,kf,fr->kqr", R, 0.5 * B[None, :] * gf.nJf[:, :, n], R)
+        VOL[:, n] = Minv @ (V.T[None] @ A)
+    if d == 1 and not skew:
+        FAC = -Minv @ np.broadcast_to(V.T @ (R.T * B[None, :]), (N_e, ra.N_p, ra.N_f))
+    else:
+        FAC = -Minv @ (V.T[None] @ (R.T[None] * (B[None, :] * gf.J_f)[:, None, :]))
+    return np.ascontiguousarray(VOL), np.ascontiguousarray(FAC)
+
+
+class DeviceResidual:
+    """Owns an ``sse_handle``: device-resident operators, geometry, state and scratch."""
+
+    def __init__(self, solver, device: int = 0, mapP: Optional[np.ndarray] = None,
+                 n_halo: int = 0, elements: Optional[np.ndarray] = None):
+        """``elements``: optional index array selecting a shard of the mesh (multi-GPU);
+        ``mapP``: (N_f, N_e_local) local connectivity override with halo slots."""
+        self.lib = load_library()
+        sd = solver.spatial_discretization
+        ra = sd.reference_approximation
+        gf = sd.geometric_factors
+        law, form = solver.law_desc, solver.form_desc
+        sel = slice(None) if elements is None else np.asarray(elements)
+        N_e = sd.N_e if elements is None else len(sel)
+        self.N_e, self.N_c, self.N_p = N_e, law["N_c"], ra.N_p
+        self.N_f, self.N_q = ra.N_f, ra.N_q
+        self._keep = []
+
+        cfg = SseConfig()
+        cfg.dim, cfg.N_p, cfg.N_q, cfg.N_f = ra.dim, ra.N_p, ra.N_q, ra.N_f
+        cfg.N_c, cfg.num_faces = law["N_c"], ra.element_type.num_faces
+        cfg.N_e, cfg.N_halo = N_e, n_halo
+        cfg.law = LAW[law["kind"]]
+        for m, am in enumerate(law.get("a", ())):
+            cfg.a[m] = am
+        cfg.b = law.get("b", 0.0)
+        cfg.gamma = law.get("gamma", 1.4)
+        cfg.form = 1 if form["kind"] == "flux_differencing" else 0
+        cfg.strategy = 1 if form["strategy"] == "physical" else 0
+        cfg.inviscid_flux = INVISCID[form["inviscid"][0]]
+        cfg.half_lambda = form["inviscid"][1] if form["inviscid"][0] == "lf" else 0.0
+        cfg.two_point_flux = 1 if form["two_point"] == "ec" else 0
+        cfg.r_is_selection = int(isinstance(ra.R, SelectionMap))
+        cfg.mass_solver = MASS[solver.mass_kind]
+        cfg.device = device
+
+        ops = SseOperators()
+        V = ra.V
+        if isinstance(V, IdentityMap):
+            cfg.v_kind = 0
+        elif isinstance(V, (WarpedTensorProductMap2D, WarpedTensorProductMap3D)):
+            cfg.v_kind = 1
+            ops.n1d = V.A.shape[0]
+            A, Bt = _f64(V.A), _f64(V.B)
+            sig = np.ascontiguousarray(V.sigma_i, dtype=np.int32)
+            self._keep += [A, Bt, sig]
+            ops.warp_A, ops.warp_B, ops.sigma_i = _dp(A), _dp(Bt), _ip(sig)
+            if isinstance(V, WarpedTensorProductMap3D):
+                Ct = _f64(V.C)
+                self._keep.append(Ct)
+                ops.warp_C = _dp(Ct)
+        else:
+            cfg.v_kind = 2
+            Vd = _f64(V.to_dense())
+            self._keep.append(Vd)
+            ops.V_dense = _dp(Vd)
+        rp, ci, val = ra.R.to_csr()
+        self._keep += [rp, ci, val]
+        ops.R_rowptr, ops.R_col, ops.R_val = _ip(rp), _ip(ci), _dp(val)
+        for m, Dm in enumerate(ra.D):
+            rp, ci, val = Dm.to_csr()
+            self._keep += [rp, ci, val]
+            ops.D_rowptr[m], ops.D_col[m], ops.D_val[m] = _ip(rp), _ip(ci), _dp(val)
+        W, B = _f64(ra.W), _f64(ra.B)
+        n_ref = _f64(gf.n_ref)
+        self._keep += [W, B, n_ref]
+        ops.W, ops.B, ops.n_ref = _dp(W), _dp(B), _dp(n_ref)
+        if not isinstance(ra.reference_mapping, NoMapping):
+            Lr = _f64(ra.reference_mapping.Lambda_ref)        # C-ordered [i][m][l]
+            Jr = _f64(ra.reference_mapping.J_ref)
+            self._keep += [Lr, Jr]
+            ops.Lambda_ref, ops.J_ref = _dp(Lr), _dp(Jr)
+        if solver.Minv is not None:
+            Mi = _f64(solver.Minv)
+            self._keep.append(Mi)
+            ops.Minv = _dp(Mi)
+
+        geo = SseGeometry()
+        Jq, Lq = _f64(gf.J_q[sel]), _f64(gf.Lambda_q[sel])
+        Jf, nJf = _f64(gf.J_f[sel]), _f64(gf.nJf[sel])
+        self._keep += [Jq, Lq, Jf, nJf]
+        geo.J_q, geo.Lambda_q, geo.J_f, geo.nJf = _dp(Jq), _dp(Lq), _dp(Jf), _dp(nJf)
+        if form["strategy"] == "physical":
+            VOL, FAC = physical_operators(solver)
+            VOL, FAC = _f64(VOL[sel]), _f64(FAC[sel])
+            self._keep += [VOL, FAC]
+            geo.VOL, geo.FAC = _dp(VOL), _dp(FAC)
+        elif solver.mass_kind == "cholesky":
+            Vd = ra.V.to_dense()
+            Mi = _f64(np.linalg.inv(np.einsum("qa,kq,qb->kab", Vd, W[None, :] * Jq, Vd)))
+            self._keep.append(Mi)
+            geo.Minv_elem = _dp(Mi)
+
+        if mapP is None:
+            if elements is not None:
+                raise ValueError("a shard needs its local mapP")
+            mapP = sd.mesh.mapP
+        mp = np.ascontiguousarray(np.asarray(mapP).T, dtype=np.int64)      # [k][j]
+        h = C.c_void_p()
+        rc = self.lib.sse_create(C.byref(cfg), C.byref(ops), C.byref(geo),
+                                 mp.ctypes.data_as(c_i64_p), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sse_create failed: " + self.lib.sse_last_error().decode())
+        self.h = h
+        self._keep = []   # everything was copied to the device
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: " + self.lib.sse_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sse_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return (self.N_e, self.N_c, self.N_p)
+
+    # ------------------------------------------------------------------ residual
+    def residual_host(self, u: np.ndarray, dudt: np.ndarray, t: float = 0.0):
+        """sse_residual with host buffers (H2D/D2H copies inside the call)."""
+        if u.dtype != np.float64 or dudt.dtype != np.float64:
+            raise TypeError("u and dudt must be Float64")
+        if u.shape != self.shape or dudt.shape != self.shape:
+            raise ValueError(f"expected arrays of shape {self.shape}")
+        if not (u.flags.c_contiguous and dudt.flags.c_contiguous):
+            raise ValueError("u and dudt must be contiguous")
+        self._check(self.lib.sse_residual(self.h, u.ctypes.data, dudt.ctypes.data, t, 0),
+                    "sse_residual")
+        return dudt
+
+    def residual_device(self, u_ptr: int, dudt_ptr: int, t: float = 0.0):
+        self._check(self.lib.sse_residual(self.h, u_ptr, dudt_ptr, t, 1), "sse_residual")
+
+    def nodal_values(self, u_ptr: int = 0):
+        self._check(self.lib.sse_nodal_values(self.h, u_ptr or None), "sse_nodal_values")
+
+    def time_derivative(self, dudt_ptr: int = 0):
+        self._check(self.lib.sse_time_derivative(self.h, dudt_ptr or None),
+                    "sse_time_derivative")
+
+    def set_state(self, u: np.ndarray):
+        u = _f64(u)
+        assert u.shape == self.shape
+        self._check(self.lib.sse_set_state(self.h, u.ctypes.data), "sse_set_state")
+
+    def get_state(self) -> np.ndarray:
+        u = np.empty(self.shape)
+        self._check(self.lib.sse_get_state(self.h, u.ctypes.data), "sse_get_state")
+        return u
+
+    def state_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.sse_state_ptr(self.h, C.byref(a), C.byref(b)), "sse_state_ptr")
+        return a.value, b.value
+
+    def rk_stage(self, a: float, b: float, dt: float):
+        self._check(self.lib.sse_rk_stage(self.h, a, b, dt), "sse_rk_stage")
+
+    def rk_step_ck54(self, dt: float):
+        self._check(self.lib.sse_rk_step_ck54(self.h, dt), "sse_rk_step_ck54")
+
+    def sync(self):
+        self._check(self.lib.sse_sync(self.h), "sse_sync")
+
+    def stream(self) -> int:
+        return self.lib.sse_stream(self.h)
+
+    def time_residual(self, reps: int, split: bool = False):
+        ms = (C.c_float * 3)()
+        self._check(self.lib.sse_time_residual(self.h, reps, int(split), ms),
+                    "sse_time_residual")
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.sse_kernel_launches(self.h))
+
+    def device_bytes(self) -> int:
+        return int(self.lib.sse_device_bytes(self.h))
+
+    # ------------------------------------------------------------------ halo
+    def halo_setup(self, send_idx: np.ndarray):
+        idx = np.ascontiguousarray(send_idx, dtype=np.int64)
+        self._check(self.lib.sse_halo_setup(self.h, idx.ctypes.data_as(c_i64_p), len(idx)),
+                    "sse_halo_setup")
+
+    def halo_buffers(self):
+        s, r = C.c_void_p(), C.c_void_p()
+        ns, nr = C.c_int64(), C.c_int64()
+        self._check(self.lib.sse_halo_buffers(self.h, C.byref(s), C.byref(r), C.byref(ns),
+                                              C.byref(nr)), "sse_halo_buffers")
+        return s.value, r.value, ns.value, nr.value
+
+    def halo_pack(self):
+        self._check(self.lib.sse_halo_pack(self.h), "sse_halo_pack")
+
+    def halo_unpack(self):
+        self._check(self.lib.sse_halo_unpack(self.h), "sse_halo_unpack")

@@ -1,0 +1,124 @@
+"""GPU parity tests: the CUDA residual behind the C-ABI vs the oracle, same inputs.
+
+Tolerance: 1e-12 relative (max-norm), the figure BASELINE.json's north_star states for FP64.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+import golden_cases as gc
+import sse_oracle as oc
+from bridge import oracle_problem
+from sse_b200.solvers import semi_discrete_residual
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def _check(solver, u, tol=TOL):
+    dudt = np.full_like(u, np.nan)
+    semi_discrete_residual(dudt, u, solver, 0.0)
+    ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+    assert np.all(np.isfinite(dudt))
+    err = _rel(dudt, ref)
+    assert err < tol, err
+    # the input must not be modified and a second call must reproduce the first
+    d2 = np.empty_like(u)
+    semi_discrete_residual(d2, u, solver, 0.0)
+    assert np.array_equal(d2, dudt)
+    return dudt
+
+
+CASES = {
+    "adv2d_tri_p4": lambda: cases.advection_tri_case(p=4, M=4, lazy=False),
+    "adv2d_tri_p2_central": lambda: cases.advection_tri_case(p=2, M=3, lazy=False, lam=0.0),
+    "euler2d_tri_p4_lf": lambda: cases.euler_tri_case(p=4, M=4, lazy=False),
+    "euler2d_tri_p3_ec": lambda: cases.euler_tri_case(p=3, M=3, lazy=False, interface="ec"),
+    "euler2d_tri_p3_nodal": lambda: cases.euler_tri_case(p=3, M=3, lazy=False, approx="nodal"),
+    "adv3d_tet_p4": lambda: cases.advection_tet_case(p=4, M=2, lazy=False),
+    "adv3d_tet_p2": lambda: cases.advection_tet_case(p=2, M=3, lazy=False),
+    "euler3d_tet_p4_lf": lambda: cases.euler_tet_case(p=4, M=2, lazy=False),
+    "euler3d_tet_p4_warp_ec": lambda: cases.euler_tet_case(p=4, M=2, lazy=False, warp=True,
+                                                           interface="ec"),
+    "euler3d_tet_p3_periodic": lambda: cases.euler_tet_case(p=3, M=2, lazy=False, warp=True,
+                                                            ic="periodic"),
+    "euler3d_tet_p2_nodal": lambda: cases.euler_tet_case(p=2, M=2, lazy=False, approx="nodal"),
+    "advdiff1d_p4": lambda: cases.advection_diffusion_case(d=1, p=4, M=4, lazy=False),
+    "advdiff1d_p8": lambda: cases.advection_diffusion_case(d=1, p=8, M=5, lazy=False),
+    "advdiff2d_p3": lambda: cases.advection_diffusion_case(d=2, p=3, M=3, lazy=False),
+    "golden_advdiff1d": lambda: gc.advection_diffusion_1d(lazy=False)[:2],
+    "golden_euler1d_gauss": lambda: gc.euler_1d_gauss(lazy=False)[:2],
+    "golden_burgers1d": lambda: gc.burgers_fluxdiff_1d(lazy=False)[:2],
+    "golden_adv2d_quad_fd": lambda: gc.advection_2d_quad_fluxdiff(lazy=False)[:2],
+    "golden_adv2d_tri": lambda: gc.advection_2d_tri(lazy=False)[:2],
+    "golden_euler_vortex": lambda: gc.euler_vortex_2d_modal(lazy=False)[:2],
+    "golden_adv3d_tet_dense_V": lambda: gc.advection_3d_tet(lazy=False)[:2],
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_residual_matches_oracle(name):
+    solver, u0 = CASES[name]()
+    try:
+        _check(solver, u0)
+        _check(solver, cases.rough_state(solver, u0, seed=1))
+    finally:
+        solver.close()
+
+
+def test_entropy_conservation_ec_flux_tet():
+    """EC two-point + EC interface flux: Σ (P w)ᵀ M dudt = 0 to round-off, and conservation."""
+    solver, u0 = cases.euler_tet_case(p=4, M=2, lazy=False, warp=True, interface="ec",
+                                      ic="periodic")
+    try:
+        u = cases.rough_state(solver, u0, seed=3)
+        dudt = np.empty_like(u)
+        semi_discrete_residual(dudt, u, solver, 0.0)
+        prob = oracle_problem(solver)
+        scale = np.sum(np.abs(dudt)) * np.max(np.abs(u))
+        assert abs(oc.entropy_residual(prob, u, dudt)) < 1e-12 * scale
+        assert np.max(np.abs(oc.conservation_residual(prob, dudt))) < 1e-12 * scale
+    finally:
+        solver.close()
+
+
+def test_fused_rk_matches_host_integration():
+    """Device-resident CK54 (fused epilogue) vs the oracle's CK54 on the golden 2-D Euler case,
+    a few steps; and the golden L2 error of the full run is reproduced on the GPU."""
+    solver, u0, T, dt, exact, gold = gc.euler_vortex_2d_modal(lazy=False)
+    try:
+        prob = oracle_problem(solver)
+        h = solver.handle
+        h.set_state(u0)
+        for _ in range(3):
+            h.rk_step_ck54(dt)
+        u_ref = oc.ck54_integrate(lambda u, t: oc.semi_discrete_residual(prob, u, t), u0,
+                                  (0.0, 3 * dt), dt)
+        assert _rel(h.get_state(), u_ref) < 1e-13
+        h.set_state(u0)
+        for _ in range(1000):
+            h.rk_step_ck54(dt)
+        u = h.get_state()
+        xq = tuple(x.T for x in solver.spatial_discretization.mesh.xyzq)
+        l2 = oc.l2_error(prob, u, np.stack(exact(*xq, T), axis=-1))
+        assert np.max(np.abs(l2 - np.array(gold))) < 1e-10, l2
+    finally:
+        solver.close()
+
+
+def test_error_paths():
+    solver, u0 = cases.advection_tri_case(p=2, M=2, lazy=False)
+    try:
+        with pytest.raises(ValueError):
+            semi_discrete_residual(np.empty((1, 1, 1)), u0, solver, 0.0)
+        with pytest.raises(TypeError):
+            semi_discrete_residual(np.empty_like(u0, dtype=np.float32),
+                                   u0.astype(np.float32), solver, 0.0)
+    finally:
+        solver.close()
