@@ -92,7 +92,7 @@ typedef struct {
   const int32_t* D_rowptr[3]; const int32_t* D_col[3]; const double* D_val[3];
   const double*  W;            /* N_q volume quadrature weights   */
   const double*  B;            /* N_f facet quadrature weights    */
-  const double*  Lambda_ref;   /* Julia Λ_ref[i,l,m] (N_q,d,d) or NULL (NoMapping)      */
+  const double*  Lambda_ref;   /* Λ_ref[i][l][m] = J dη_l/dξ_m, C-ordered (N_q,d,d), or NULL (NoMapping) */
   const double*  J_ref;        /* N_q or NULL                                           */
   const double*  n_ref;        /* (num_faces x d) row-major reference face normals      */
   const double*  Minv;         /* (N_p x N_p) row-major M^-1 of WeightAdjustedSolver, or NULL = I */
@@ -128,6 +128,10 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
 int sse_nodal_values(sse_handle* h, const double* u_dev);
 int sse_time_derivative(sse_handle* h, double* dudt_dev);
 
+/* Loop B on the local element range [k_begin, k_end) only (interior/boundary split that
+ * overlaps the halo exchange). */
+int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end);
+
 /* Device-resident state and fused low-storage (2N) Runge-Kutta:
  *   k <- a*k + dt*R(u);  u <- u + b*k   (evaluated in the residual kernel's epilogue). */
 int sse_set_state(sse_handle* h, const double* u_host);
@@ -146,12 +150,21 @@ int sse_halo_pack(sse_handle* h);      /* traces -> send buffer (after sse_nodal
 int sse_halo_unpack(sse_handle* h);    /* recv buffer -> halo trace slots                     */
 
 /* Streams / timing / introspection. */
+/* Asynchronous (stream-ordered) H2D of the state / D2H of dudt (the latter synchronises). */
+int sse_upload_state(sse_handle* h, const double* u_host);
+int sse_download_dudt(sse_handle* h, double* dudt_host);
+/* Run all kernels/copies of this handle on an external cudaStream_t (e.g. the stream the host
+ * framework orders its NCCL operations against) instead of the handle's own stream. */
+int sse_set_stream(sse_handle* h, void* stream);
 int sse_sync(sse_handle* h);
 void* sse_stream(sse_handle* h);                         /* cudaStream_t the kernels run on */
 /* Runs `reps` residuals on the device-resident state, timed with CUDA events on the
  * library's stream; ms[0] = total, ms[1] = loop-A kernels, ms[2] = loop-B kernels (the
  * split is measured in a second pass when split != 0). */
 int sse_time_residual(sse_handle* h, int reps, int split, float* ms);
+/* FP64 FMA-chain microbenchmark (TFLOP/s, FMA = 2 flops): roofline denominator for the
+ * FP64-bound flux-differencing kernel. */
+int sse_measure_fp64_peak(int device, double* tflops);
 int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
 int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
 

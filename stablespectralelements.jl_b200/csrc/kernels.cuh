@@ -33,7 +33,8 @@ struct Tables {
 };
 
 struct Geo {
-  long long N_e;
+  long long N_e;      // one past the last element this launch may touch
+  long long k_begin;  // first element of this launch (element-range launches)
   const double *J_q, *L_q, *J_f, *nJf;
   const int *toff;      // trace offset of the exterior node: (k'*N_c)*N_f + j'
   const int *mapP;      // raw linear index j' + N_f*k'
@@ -326,7 +327,7 @@ k_nodal_values(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   double* bufQ2 = bufQ + E * NC * Nq;
   double* bufF = bufQ2 + E * NC * Nq;
   double* tmp = bufF + E * NC * Nf;
-  const long long k0 = (long long)blockIdx.x * E;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);   // valid elements in this CTA
 
   SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? u[k0 * NC * Np + idx] : 1.0;
@@ -433,7 +434,7 @@ k_fluxdiff(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   double* sR = sNf + E * Nf * DIM;
   double* sM = sR + E * NC * Nq;
   double* sD = sM + E * NC * Np;
-  const long long k0 = (long long)blockIdx.x * E;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
   // ---- phase 0: stage nodal states and metric terms
@@ -583,7 +584,7 @@ k_standard_ref(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   double* sR = sFf + E * NC * Nf;
   double* sM = sR + E * NC * Nq;
   double* tmp = sM + E * NC * Np;
-  const long long k0 = (long long)blockIdx.x * E;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
 
   // ---- phase 0: physical flux at volume nodes, collapsed metrics, g_m
   SSE_LOOP(idx, E * Nq) {
@@ -706,7 +707,7 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   double* sP = sFn + E * DIM * NC * Nf;          // [E][D][NC][N_p]
   double* sQ = sP + E * DIM * NC * Np;           // [E][D][NC][N_q]
   double* tmp = sQ + E * DIM * NC * Nq;
-  const long long k0 = (long long)blockIdx.x * E;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
   if (stage == 0) {
@@ -816,12 +817,12 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
 }
 
 // ------------------------------------------------------------------------- halo
-// send[c*n + s] = u_f[off(idx[s]) + c*N_f]
+// send[s*NC + c] = u_f[off(idx[s]) + c*N_f]  (node-major: per-peer segments are contiguous)
 __global__ void k_halo_pack(const double* __restrict__ u_f, const int* __restrict__ off, int n,
                             int NC, int Nf, double* __restrict__ send) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n)
-    for (int c = 0; c < NC; ++c) send[(long long)c * n + s] = u_f[off[s] + (long long)c * Nf];
+    for (int c = 0; c < NC; ++c) send[(long long)s * NC + c] = u_f[off[s] + (long long)c * Nf];
 }
 
 // halo slot h lives at pseudo-element N_e + h / N_f, node h % N_f
@@ -831,7 +832,7 @@ __global__ void k_halo_unpack(double* __restrict__ u_f, const double* __restrict
   if (h < n) {
     long long kk = N_e + h / Nf;
     int j = h % Nf;
-    for (int c = 0; c < NC; ++c) u_f[(kk * NC + c) * Nf + j] = recv[(long long)c * n + h];
+    for (int c = 0; c < NC; ++c) u_f[(kk * NC + c) * Nf + j] = recv[(long long)h * NC + c];
   }
 }
 

@@ -1,0 +1,584 @@
+// Compile-time specialised kernels for tensor-product elements (Tri/Tet in collapsed
+// coordinates, Quad/Hex): N1 = p + 1 nodes per direction, N_q = N1^DIM, known at compile time so
+// that all index arithmetic folds to constants and the contraction loops unroll.
+//
+// Loop B (flux-differencing form) differs from the generic kernel in two ways:
+//  * volume term: the S_m couple only nodes on the same tensor line (the Kronecker structure of
+//    D_eta), so each thread (= volume node) evaluates the pairs with its cyclic successors at
+//    offsets 1..N1/2 along each direction and hands the result to the partner through shared
+//    memory.  Every unordered pair is evaluated exactly once -- d*N1^d*(N1-1)/2 two-point
+//    fluxes instead of twice that (flux_differencing_form.jl:10-34 does the same pairwise).
+//  * facet correction: C = R^T B has the same number KC of entries in every row (one facet node
+//    per non-collapsed face, N1 on the collapsed one), stored in ELL format.
+#pragma once
+#include "kernels.cuh"
+
+namespace sse {
+
+struct FastTables {
+  const double* Sp;    // [DIM][H][DIM][NQ]: S_m[i, partner(i; l, o)]
+  const int* Cj;       // [KC][NQ] facet node of ELL slot k
+  const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
+  const double* Rv;    // [KC][NQ] R[j, i]
+  const int* Rred;     // per R-CSR entry: k * NQ + i  (slot of the facet-correction term)
+};
+
+__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// ---------------------------------------------------------------- sum-factorised V, V^T
+// src [E][NC][N_p] -> dst [E][NC][NQ]; every thread carries all NC components of one output.
+template <int DIM, int N1, int NC>
+__device__ __forceinline__ void apply_V_t(const Tables& T, int E, const double* __restrict__ src,
+                                          double* __restrict__ dst, double* __restrict__ tmp) {
+  constexpr int NQ = ipow(N1, DIM);
+  const int Np = T.N_p;
+  if (T.v_kind == V_IDENTITY) {
+    SSE_LOOP(idx, E * NC * NQ) dst[idx] = src[idx];
+    __syncthreads();
+    return;
+  }
+  if (T.v_kind == V_DENSE) {
+    SSE_LOOP(idx, E * NQ) {
+      int i = idx % NQ, e = idx / NQ;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+      for (int p = 0; p < Np; ++p) {
+        double v = __ldg(T.Vd + i * Np + p);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * Np + p], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dst[(e * NC + c) * NQ + i] = acc[c];
+    }
+    __syncthreads();
+    return;
+  }
+  if constexpr (DIM == 2) {
+    constexpr int N2 = N1 * N1;
+    double* Z = tmp;  // [E][NC][b1][a2]
+    SSE_LOOP(idx, E * N2) {
+      int a2 = idx % N1, b1 = (idx / N1) % N1, e = idx / N2;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < N1; ++b2)
+        if (b2 < N1 - b1) {
+          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
+          int si = __ldg(T.sig + b1 * N1 + b2);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * Np + si], acc[c]);
+        }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N2 + b1 * N1 + a2] = acc[c];
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N2) {
+      int a2 = idx % N1, a1 = (idx / N1) % N1, e = idx / N2;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int b1 = 0; b1 < N1; ++b1) {
+        double v = __ldg(T.wA + a1 * N1 + b1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, Z[(e * NC + c) * N2 + b1 * N1 + a2], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dst[(e * NC + c) * NQ + a1 * N1 + a2] = acc[c];
+    }
+    __syncthreads();
+  } else if constexpr (DIM == 3) {
+    constexpr int N2 = N1 * N1, N3 = N1 * N1 * N1;
+    double* Z = tmp;                 // [E][NC][b1][b2][a3]
+    double* Wt = tmp + E * NC * N3;  // [E][NC][b1][a2][a3]
+    SSE_LOOP(idx, E * N3) {
+      int a3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
+      if (b2 < N1 - b1) {
+        double acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int b3 = 0; b3 < N1; ++b3)
+          if (b3 < N1 - b1 - b2) {
+            double v = __ldg(T.wC + ((a3 * N1 + b1) * N1 + b2) * N1 + b3);
+            int si = __ldg(T.sig + (b1 * N1 + b2) * N1 + b3);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * Np + si], acc[c]);
+          }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3] = acc[c];
+      }
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N3) {
+      int a3 = idx % N1, a2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < N1; ++b2)
+        if (b2 < N1 - b1) {
+          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            acc[c] = fma(v, Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3], acc[c]);
+        }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Wt[(e * NC + c) * N3 + (b1 * N1 + a2) * N1 + a3] = acc[c];
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N3) {
+      int a23 = idx % N2, a1 = (idx / N2) % N1, e = idx / N3;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int b1 = 0; b1 < N1; ++b1) {
+        double v = __ldg(T.wA + a1 * N1 + b1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, Wt[(e * NC + c) * N3 + b1 * N2 + a23], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dst[(e * NC + c) * NQ + a1 * N2 + a23] = acc[c];
+    }
+    __syncthreads();
+  }
+}
+
+// src [E][NC][NQ] -> dst [E][NC][N_p]
+template <int DIM, int N1, int NC>
+__device__ __forceinline__ void apply_Vt_t(const Tables& T, int E, const double* __restrict__ src,
+                                           double* __restrict__ dst, double* __restrict__ tmp) {
+  constexpr int NQ = ipow(N1, DIM);
+  const int Np = T.N_p;
+  if (T.v_kind == V_IDENTITY) {
+    SSE_LOOP(idx, E * NC * NQ) dst[idx] = src[idx];
+    __syncthreads();
+    return;
+  }
+  if (T.v_kind == V_DENSE) {
+    SSE_LOOP(idx, E * Np) {
+      int p = idx % Np, e = idx / Np;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+      for (int i = 0; i < NQ; ++i) {
+        double v = __ldg(T.VdT + p * NQ + i);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + i], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Np + p] = acc[c];
+    }
+    __syncthreads();
+    return;
+  }
+  if constexpr (DIM == 2) {
+    constexpr int N2 = N1 * N1;
+    double* Z = tmp;  // [E][NC][b1][a2]
+    SSE_LOOP(idx, E * N2) {
+      int a2 = idx % N1, b1 = (idx / N1) % N1, e = idx / N2;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int a1 = 0; a1 < N1; ++a1) {
+        double v = __ldg(T.wA + a1 * N1 + b1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + a1 * N1 + a2], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N2 + b1 * N1 + a2] = acc[c];
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N2) {
+      int b2 = idx % N1, b1 = (idx / N1) % N1, e = idx / N2;
+      if (b2 < N1 - b1) {
+        double acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int a2 = 0; a2 < N1; ++a2) {
+          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) acc[c] = fma(v, Z[(e * NC + c) * N2 + b1 * N1 + a2], acc[c]);
+        }
+        int si = __ldg(T.sig + b1 * N1 + b2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Np + si] = acc[c];
+      }
+    }
+    __syncthreads();
+  } else if constexpr (DIM == 3) {
+    constexpr int N2 = N1 * N1, N3 = N1 * N1 * N1;
+    double* Wt = tmp;               // [E][NC][b1][a2][a3]
+    double* Z = tmp + E * NC * N3;  // [E][NC][b1][b2][a3]
+    SSE_LOOP(idx, E * N3) {
+      int a23 = idx % N2, b1 = (idx / N2) % N1, e = idx / N3;
+      double acc[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int a1 = 0; a1 < N1; ++a1) {
+        double v = __ldg(T.wA + a1 * N1 + b1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + a1 * N2 + a23], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Wt[(e * NC + c) * N3 + b1 * N2 + a23] = acc[c];
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N3) {
+      int a3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
+      if (b2 < N1 - b1) {
+        double acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int a2 = 0; a2 < N1; ++a2) {
+          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            acc[c] = fma(v, Wt[(e * NC + c) * N3 + (b1 * N1 + a2) * N1 + a3], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3] = acc[c];
+      }
+    }
+    __syncthreads();
+    SSE_LOOP(idx, E * N3) {
+      int b3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
+      if (b2 < N1 - b1 && b3 < N1 - b1 - b2) {
+        double acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int a3 = 0; a3 < N1; ++a3) {
+          double v = __ldg(T.wC + ((a3 * N1 + b1) * N1 + b2) * N1 + b3);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            acc[c] = fma(v, Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3], acc[c]);
+        }
+        int si = __ldg(T.sig + (b1 * N1 + b2) * N1 + b3);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Np + si] = acc[c];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread
+template <int NQ, int NC>
+__device__ __forceinline__ void apply_R_t(const Tables& T, int E, const double* __restrict__ src,
+                                          double* __restrict__ dst) {
+  const int Nf = T.N_f;
+  SSE_LOOP(idx, E * Nf) {
+    int j = idx % Nf, e = idx / Nf;
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    const int b = __ldg(T.R_rp + j), en = __ldg(T.R_rp + j + 1);
+    for (int q = b; q < en; ++q) {
+      double v = __ldg(T.R_v + q);
+      int i = __ldg(T.R_ci + q);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + i], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Nf + j] = acc[c];
+  }
+  __syncthreads();
+}
+
+// weight-adjusted (M^-1 = I) or diagonal mass solve, in place on rhs [E][NC][N_p]
+template <int DIM, int N1, int NC>
+__device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long long k0, int E,
+                                             double* __restrict__ rhs, double* __restrict__ q,
+                                             double* __restrict__ tmp) {
+  constexpr int NQ = ipow(N1, DIM);
+  if (T.mass_kind == MASS_DIAGONAL) {
+    SSE_LOOP(idx, E * NC * NQ) {
+      int i = idx % NQ, e = idx / (NQ * NC);
+      long long k = min(k0 + e, G.N_e - 1);
+      rhs[idx] = fdiv(rhs[idx], T.W[i] * G.J_q[k * NQ + i]);
+    }
+    __syncthreads();
+    return;
+  }
+  apply_V_t<DIM, N1, NC>(T, E, rhs, q, tmp);
+  SSE_LOOP(idx, E * NQ) {
+    int i = idx % NQ, e = idx / NQ;
+    long long k = min(k0 + e, G.N_e - 1);
+    double sc = fdiv(__ldg(T.W + i), G.J_q[k * NQ + i]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) q[(e * NC + c) * NQ + i] *= sc;
+  }
+  __syncthreads();
+  apply_Vt_t<DIM, N1, NC>(T, E, q, rhs, tmp);
+}
+
+// =========================================================================== loop A
+// shared: bufP[E*NC*N_p] | bufQ[E*NC*NQ] | bufQ2[E*NC*NQ] | bufF[E*NC*N_f] | tmp[2*E*NC*NQ]
+template <int DIM, int N1, int LAW>
+__global__ void __launch_bounds__(256)
+k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
+               double* __restrict__ u_f, int E, int proj) {
+  constexpr int NC = LawTraits<DIM, LAW>::NC;
+  constexpr int NQ = ipow(N1, DIM);
+  extern __shared__ double sm[];
+  const int Np = T.N_p, Nf = T.N_f;
+  double* bufP = sm;
+  double* bufQ = bufP + E * NC * Np;
+  double* bufQ2 = bufQ + E * NC * NQ;
+  double* bufF = bufQ2 + E * NC * NQ;
+  double* tmp = bufF + E * NC * Nf;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
+  const int Ev = (int)min((long long)E, G.N_e - k0);
+
+  SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? u[k0 * NC * Np + idx] : 1.0;
+  __syncthreads();
+  apply_V_t<DIM, N1, NC>(T, E, bufP, bufQ, tmp);
+  if (proj == 0) {
+    apply_R_t<NQ, NC>(T, E, bufQ, bufF);
+    SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
+    SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
+    return;
+  }
+  SSE_LOOP(idx, E * NQ) {
+    int i = idx % NQ, e = idx / NQ;
+    double uu[NC], w[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) uu[c] = bufQ[(e * NC + c) * NQ + i];
+    cons_to_entropy<DIM, LAW>(P, uu, w);
+    double sc = 1.0;
+    if (proj == 2) {
+      long long k = min(k0 + e, G.N_e - 1);
+      sc = __ldg(T.W + i) * G.J_q[k * NQ + i];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) bufQ2[(e * NC + c) * NQ + i] = w[c] * sc;
+  }
+  __syncthreads();
+  if (proj == 2) {
+    apply_Vt_t<DIM, N1, NC>(T, E, bufQ2, bufP, tmp);
+    mass_solve_t<DIM, N1, NC>(T, G, k0, E, bufP, bufQ2, tmp);
+    apply_V_t<DIM, N1, NC>(T, E, bufP, bufQ2, tmp);
+  }
+  apply_R_t<NQ, NC>(T, E, bufQ2, bufF);
+  if (proj == 2) {
+    SSE_LOOP(idx, Ev * NQ) {
+      int i = idx % NQ, e = idx / NQ;
+      double w[NC], uu[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) w[c] = bufQ2[(e * NC + c) * NQ + i];
+      entropy_to_cons<DIM, LAW>(P, w, uu);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) u_q[((k0 + e) * NC + c) * NQ + i] = uu[c];
+    }
+  } else {
+    SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
+  }
+  SSE_LOOP(idx, Ev * Nf) {
+    int j = idx % Nf, e = idx / Nf;
+    double w[NC], uu[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) w[c] = bufF[(e * NC + c) * Nf + j];
+    entropy_to_cons<DIM, LAW>(P, w, uu);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) u_f[((k0 + e) * NC + c) * Nf + j] = uu[c];
+  }
+}
+
+// ==================================================== loop B, flux-differencing form
+// shared (doubles): sS[NS][E*NQ] | sL[DD][E*NQ] | sSf[NS][E*NF] | sNf[DIM][E*NF] |
+//                   sFf[E][NC][NF] | sR[E][NC][NQ] | sM[E][NC][NP] | sX[max(2*H*NC, KC*NC, 2*NC)*E*NQ]
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(256)
+k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
+                  const double* __restrict__ u_f, double* __restrict__ dudt, int E) {
+  constexpr int NC = LawTraits<DIM, LAW>::NC;
+  constexpr int NS = LawTraits<DIM, LAW>::NS;
+  constexpr int NQ = ipow(N1, DIM);
+  constexpr int DD = DIM * DIM;
+  constexpr int H = N1 / 2;
+  extern __shared__ double sm[];
+  const int Np = T.N_p, Nf = T.N_f;
+  const int nq = E * NQ, nf = E * Nf;
+  double* sS = sm;
+  double* sL = sS + NS * nq;
+  double* sSf = sL + DD * nq;
+  double* sNf = sSf + NS * nf;
+  double* sFf = sNf + DIM * nf;
+  double* sR = sFf + NC * nf;
+  double* sM = sR + NC * nq;
+  double* sX = sM + E * NC * Np;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
+  const int tid = threadIdx.x;
+  const bool active = tid < nq;
+  const int e = active ? tid / NQ : 0;
+  const int i = active ? tid % NQ : 0;
+
+  double si[NS], Li[DD], r[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) r[c] = 0.0;
+
+  // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
+  if (active) {
+    long long k = min(k0 + e, G.N_e - 1);
+    double uu[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) uu[c] = u_q[(k * NC + c) * NQ + i];
+    cons_to_state<DIM, LAW>(P, uu, si);
+#pragma unroll
+    for (int c = 0; c < NS; ++c) sS[c * nq + tid] = si[c];
+#pragma unroll
+    for (int c = 0; c < DD; ++c) {
+      Li[c] = G.L_q[(k * DD + c) * NQ + i];
+      sL[c * nq + tid] = Li[c];
+    }
+  }
+  // ---- phase 1: interface numerical flux at the facet nodes
+  SSE_LOOP(idx, nf) {
+    int j = idx % Nf, ee = idx / Nf;
+    long long k = min(k0 + ee, G.N_e - 1);
+    long long gj = k * Nf + j;
+    double nJ[DIM], nfv[DIM], sl[NS], fs[NC];
+    double iJf = __drcp_rn(G.J_f[gj]);
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      nJ[m] = G.nJf[gj * DIM + m];
+      nfv[m] = nJ[m] * iJf;
+    }
+    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * Nf + j, G.toff[gj], Nf, nfv, sl, fs);
+    double bj = __ldg(T.B + j) * G.J_f[gj];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * Nf + j] = bj * fs[c];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) sSf[c * nf + idx] = sl[c];
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) sNf[m * nf + idx] = 0.5 * nJ[m];
+  }
+  __syncthreads();
+
+  // ---- phase 2: volume flux differencing, every pair on a tensor line evaluated once
+#pragma unroll
+  for (int l = 0; l < DIM; ++l) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int stride = (l == 0) ? ipow(N1, DIM - 1) : (l == 1 ? ipow(N1, DIM - 2) : 1);
+    const int al = (i / stride) % N1;
+    double* buf = sX + (l & 1) * (H * NC * nq);
+    if (active) {
+#pragma unroll
+      for (int o = 1; o <= H; ++o) {
+        const bool mine = (2 * o < N1) || (al < N1 / 2);
+        if (mine) {
+          int ap = al + o;
+          if (ap >= N1) ap -= N1;
+          const int jt = tid + (ap - al) * stride;
+          double cv[DIM], sj[NS], f[NC];
+#pragma unroll
+          for (int n = 0; n < DIM; ++n) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < DIM; ++m) {
+              const bool used = COLLAPSED ? (m >= l) : (m == l);
+              if (used)
+                acc = fma(__ldg(F.Sp + ((l * H + (o - 1)) * DIM + m) * NQ + i),
+                          Li[m + DIM * n] + sL[(m + DIM * n) * nq + jt], acc);
+            }
+            cv[n] = acc;
+          }
+#pragma unroll
+          for (int c = 0; c < NS; ++c) sj[c] = sS[c * nq + jt];
+          two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, cv, f);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            r[c] -= f[c];
+            buf[((o - 1) * NC + c) * nq + tid] = f[c];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int o = 1; o <= H; ++o) {
+        const bool theirs = (2 * o < N1) || (al >= N1 / 2);
+        if (theirs) {
+          int as = al - o;
+          if (as < 0) as += N1;
+          const int jt = tid + (as - al) * stride;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) r[c] += buf[((o - 1) * NC + c) * nq + jt];
+        }
+      }
+    }
+  }
+  __syncthreads();   // all reads of the pair buffers are done before sX is reused
+
+  // ---- phase 3: facet correction (ELL rows of C = R^T B)
+  if (active && !T.r_is_selection) {
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const int j = __ldg(F.Cj + kk * NQ + i);
+      const double cij = __ldg(F.Cv + kk * NQ + i);
+      const int fc = j / T.npf;
+      const int jj = e * Nf + j;
+      double nJ[DIM], sj[NS], f[NC];
+#pragma unroll
+      for (int n = 0; n < DIM; ++n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
+        nJ[n] = fma(0.5, acc, sNf[n * nf + jj]);
+      }
+#pragma unroll
+      for (int c = 0; c < NS; ++c) sj[c] = sSf[c * nf + jj];
+      two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double dlt = cij * f[c];
+        r[c] -= dlt;
+        sX[(kk * NC + c) * nq + tid] = dlt;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 4: f_f -= column sums of the facet-correction terms
+  if (!T.r_is_selection) {
+    SSE_LOOP(idx, NC * nf) {
+      int j = idx % Nf, c = (idx / Nf) % NC, ee = idx / (Nf * NC);
+      double acc = 0.0;
+      const int b = __ldg(T.R_rp + j), en = __ldg(T.R_rp + j + 1);
+      for (int q = b; q < en; ++q) {
+        int pk = __ldg(F.Rred + q);
+        acc += sX[((pk / NQ) * NC + c) * nq + ee * NQ + (pk % NQ)];
+      }
+      sFf[idx] -= acc;
+    }
+    __syncthreads();
+  }
+  // ---- phase 5: r_q -= R^T f_f (ELL), then hand r_q to the modal projection
+  if (active) {
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const int j = __ldg(F.Cj + kk * NQ + i);
+      const double rv = __ldg(F.Rv + kk * NQ + i);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, sFf[(e * NC + c) * Nf + j], r[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
+  }
+  __syncthreads();
+  // ---- phase 6: dudt = M^-1 V^T r_q
+  apply_Vt_t<DIM, N1, NC>(T, E, sR, sM, sX);
+  mass_solve_t<DIM, N1, NC>(T, G, k0, E, sM, sR, sX);
+  store_result(T, G, rk, k0, E, NC, sM, dudt);
+}
+
+}  // namespace sse

@@ -30,15 +30,38 @@ template <int DIM, int LAW> struct LawTraits {
   static constexpr int NS = (LAW == LAW_EULER) ? DIM + 3 : 1;
 };
 
+// a / b through the correctly rounded reciprocal (MUFU.RCP64H + Newton steps, no slow path):
+// <= 1 ulp from IEEE division, far inside the 1e-12 parity budget.
+__device__ __forceinline__ double fdiv(double a, double b) { return a * __drcp_rn(b); }
+
+// logmean / inv_logmean (ConservationLaws.jl:132-156).  With q = (x-y)^2, t = (x+y)^2 the
+// reference's f^2 equals q/t and its Taylor branch (x+y)*105/(210 + f2(70 + f2(42 + 30 f2)))
+// becomes 105 (x+y) t^3 / (210 t^3 + 70 q t^2 + 42 q^2 t + 30 q^3): one division instead of
+// two.  The branch test f2 < 1e-4 is q < 1e-4 t; both branches agree to ~2e-17 relative at
+// the threshold, so a flipped decision for borderline arguments is harmless.
+__device__ __forceinline__ void logmean_terms(double x, double y, double& num, double& den,
+                                              bool& taylor) {
+  double d = x - y, s = x + y;
+  double q = d * d, t = s * s;
+  taylor = q < 1.0e-4 * t;
+  double q2 = q * q;
+  den = fma(t, fma(t, fma(210.0, t, 70.0 * q), 42.0 * q2), 30.0 * q * q2);
+  num = 105.0 * s * t * t * t;
+}
+
 __device__ __forceinline__ double logmean(double x, double y) {
-  double f2 = (x * (x - 2.0 * y) + y * y) / (x * (x + 2.0 * y) + y * y);
-  if (f2 < 1.0e-4) return (x + y) * 105.0 / (210.0 + f2 * (70.0 + f2 * (42.0 + f2 * 30.0)));
+  double num, den;
+  bool taylor;
+  logmean_terms(x, y, num, den, taylor);
+  if (taylor) return fdiv(num, den);
   return (y - x) / log(y / x);
 }
 
 __device__ __forceinline__ double inv_logmean(double x, double y) {
-  double f2 = (x * (x - 2.0 * y) + y * y) / (x * (x + 2.0 * y) + y * y);
-  if (f2 < 1.0e-4) return (210.0 + f2 * (70.0 + f2 * (42.0 + f2 * 30.0))) / ((x + y) * 105.0);
+  double num, den;
+  bool taylor;
+  logmean_terms(x, y, num, den, taylor);
+  if (taylor) return fdiv(den, num);
   return log(y / x) / (y - x);
 }
 
@@ -47,16 +70,17 @@ template <int DIM, int LAW>
 __device__ __forceinline__ void cons_to_state(const Phys& P, const double* u, double* s) {
   if constexpr (LAW == LAW_EULER) {
     double rho = u[0];
+    double irho = __drcp_rn(rho);
     double k = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) {
-      s[1 + m] = u[1 + m] / rho;
+      s[1 + m] = u[1 + m] * irho;
       k += s[1 + m] * s[1 + m];
     }
     double p = (P.gamma - 1.0) * (u[DIM + 1] - 0.5 * rho * k);
     s[0] = rho;
     s[DIM + 1] = p;
-    s[DIM + 2] = rho / p;
+    s[DIM + 2] = fdiv(rho, p);
   } else {
     s[0] = u[0];
   }
@@ -159,8 +183,9 @@ __device__ __forceinline__ double wave_speed(const Phys& P, const double* L, con
       vnl += L[1 + m] * n[m];
       vnr += R[1 + m] * n[m];
     }
-    double cl = sqrt(P.gamma * L[DIM + 1] / L[0]);
-    double cr = sqrt(P.gamma * R[DIM + 1] / R[0]);
+    // c^2 = gamma p / rho = gamma / (rho/p)
+    double cl = sqrt(fdiv(P.gamma, L[DIM + 2]));
+    double cr = sqrt(fdiv(P.gamma, R[DIM + 2]));
     return fmax(fabs(vnl), fabs(vnr)) + fmax(cl, cr);
   } else {
     double an = 0.0;
@@ -181,8 +206,9 @@ __device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, 
     for (int m = 0; m < DIM; ++m) k += u[1 + m] * u[1 + m];
     k *= 0.5 / u[0];
     double p = gm1 * (u[DIM + 1] - k);
-    double inv_p = 1.0 / p;
-    w[0] = (g - log(p / pow(u[0], g))) / gm1 - k * inv_p;
+    double inv_p = __drcp_rn(p);
+    // log(p / rho^gamma) = log p - gamma log rho (two logs instead of pow + log)
+    w[0] = (g - (log(p) - g * log(u[0]))) / gm1 - k * inv_p;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) w[1 + m] = u[1 + m] * inv_p;
     w[DIM + 1] = -u[0] * inv_p;
@@ -201,9 +227,10 @@ __device__ __forceinline__ void entropy_to_cons(const Phys& P, const double* w_i
     double k = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) k += w[1 + m] * w[1 + m];
-    k /= (2.0 * w[DIM + 1]);
+    k = fdiv(k, 2.0 * w[DIM + 1]);
     double s = g - w[0] + k;
-    double rho_e = pow(gm1 / pow(-w[DIM + 1], g), inv_gm1) * exp(-s * inv_gm1);
+    // ((gm1 / (-w_last)^g)^(1/gm1)) exp(-s/gm1) = exp((log gm1 - g log(-w_last) - s) / gm1)
+    double rho_e = exp((log(gm1) - g * log(-w[DIM + 1]) - s) * inv_gm1);
     u[0] = -w[DIM + 1] * rho_e;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) u[1 + m] = w[1 + m] * rho_e;

@@ -10,12 +10,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/sse_b200.h"
 #include "kernels.cuh"
+#include "kernels_tensor.cuh"
 
 using namespace sse;
 
@@ -45,6 +47,7 @@ struct sse_handle {
   Geo G{};
   Phys P{};
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> allocs;
   int64_t bytes = 0;
@@ -61,6 +64,9 @@ struct sse_handle {
   int second_order = 0, proj = 0, law_t = 0;
   int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
   size_t smem_a = 0, smem_b = 0;
+  // compile-time specialised tensor-product path
+  FastTables F{};
+  int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
 };
 
 template <typename Tp>
@@ -134,7 +140,7 @@ template <int DIM, int LAW>
 static int launch_a(sse_handle* h, const double* u_dev) {
   CU(cudaFuncSetAttribute(k_nodal_values<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)h->smem_a));
-  int grid = (int)((h->cfg.N_e + h->E_a - 1) / h->E_a);
+  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_a - 1) / h->E_a);
   k_nodal_values<DIM, LAW><<<grid, h->thr_a, h->smem_a, h->stream>>>(h->T, h->G, h->P, u_dev,
                                                                      h->u_q, h->u_f, h->E_a,
                                                                      h->proj);
@@ -145,7 +151,7 @@ static int launch_a(sse_handle* h, const double* u_dev) {
 
 template <int DIM, int LAW>
 static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
-  int grid = (int)((h->cfg.N_e + h->E_b - 1) / h->E_b);
+  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_b - 1) / h->E_b);
   if (h->cfg.strategy == SSE_PHYSICAL_OPERATOR) {
     CU(cudaFuncSetAttribute(k_physical<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)h->smem_b));
@@ -188,8 +194,71 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
     default: return fail("unsupported dim/law combination");                         \
   }
 
-static int run_a(sse_handle* h, const double* u_dev) { SSE_DISPATCH(launch_a, h, u_dev); }
+template <int DIM, int N1, int LAW>
+static int launch_a_fast(sse_handle* h, const double* u_dev) {
+  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_a));
+  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_a - 1) / h->E_a);
+  k_nodal_tensor<DIM, N1, LAW><<<grid, h->thr_a, h->smem_a, h->stream>>>(
+      h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->E_a, h->proj);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
+  CU(cudaFuncSetAttribute(k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_b));
+  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_b - 1) / h->E_b);
+  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->E_b);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// instantiated (dim, n1, law) combinations of the specialised kernels
+static int fast_a_key(int dim, int n1, int law) {
+  if ((dim == 2 || dim == 3) && n1 >= 3 && n1 <= 5 && (law == LAW_EULER || law == LAW_ADV))
+    return dim * 100 + n1 * 10 + law;
+  return 0;
+}
+static int fast_b_key(int dim, int n1, int law, int collapsed, int kc) {
+  if (law != LAW_EULER || !collapsed || n1 < 3 || n1 > 5) return 0;
+  if (dim == 3 && kc == 3 + n1) return 300 + n1;
+  if (dim == 2 && kc == 3) return 200 + n1;
+  return 0;
+}
+
+static int run_a(sse_handle* h, const double* u_dev) {
+  switch (h->fast_a) {
+    case 232: return launch_a_fast<2, 3, LAW_EULER>(h, u_dev);
+    case 242: return launch_a_fast<2, 4, LAW_EULER>(h, u_dev);
+    case 252: return launch_a_fast<2, 5, LAW_EULER>(h, u_dev);
+    case 332: return launch_a_fast<3, 3, LAW_EULER>(h, u_dev);
+    case 342: return launch_a_fast<3, 4, LAW_EULER>(h, u_dev);
+    case 352: return launch_a_fast<3, 5, LAW_EULER>(h, u_dev);
+    case 230: return launch_a_fast<2, 3, LAW_ADV>(h, u_dev);
+    case 240: return launch_a_fast<2, 4, LAW_ADV>(h, u_dev);
+    case 250: return launch_a_fast<2, 5, LAW_ADV>(h, u_dev);
+    case 330: return launch_a_fast<3, 3, LAW_ADV>(h, u_dev);
+    case 340: return launch_a_fast<3, 4, LAW_ADV>(h, u_dev);
+    case 350: return launch_a_fast<3, 5, LAW_ADV>(h, u_dev);
+    default: break;
+  }
+  SSE_DISPATCH(launch_a, h, u_dev);
+}
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
+  switch (h->fast_b) {
+    case 203: return launch_b_fast<2, 3, LAW_EULER, true, 3>(h, dudt_dev, rk);
+    case 204: return launch_b_fast<2, 4, LAW_EULER, true, 3>(h, dudt_dev, rk);
+    case 205: return launch_b_fast<2, 5, LAW_EULER, true, 3>(h, dudt_dev, rk);
+    case 303: return launch_b_fast<3, 3, LAW_EULER, true, 6>(h, dudt_dev, rk);
+    case 304: return launch_b_fast<3, 4, LAW_EULER, true, 7>(h, dudt_dev, rk);
+    case 305: return launch_b_fast<3, 5, LAW_EULER, true, 8>(h, dudt_dev, rk);
+    default: break;
+  }
   SSE_DISPATCH(launch_b, h, dudt_dev, rk);
 }
 
@@ -206,7 +275,7 @@ int sse_destroy(sse_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
@@ -377,6 +446,69 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       if (dev_upload_vec(h, A.rp, &T.S_rp) || dev_upload_vec(h, A.ci, &T.S_ci) ||
           dev_upload_vec(h, A.v, &T.S_v))
         return -1;
+
+      // ---- tensor-product fast path: line-pair tables for S, ELL tables for C = R^T B
+      const int n1 = ops->n1d;
+      size_t nd1 = 1;
+      for (int m = 0; m < d; ++m) nd1 *= (size_t)std::max(n1, 1);
+      int kc = Nq > 0 ? Rt.rp[1] - Rt.rp[0] : 0;
+      bool uniform = true;
+      for (int i = 0; i < Nq; ++i) uniform = uniform && (Rt.rp[i + 1] - Rt.rp[i] == kc);
+      const bool collapsed = !Gref.empty();
+      bool ok = d >= 2 && n1 >= 2 && (int)nd1 == Nq && uniform && kc > 0 && !cfg->r_is_selection &&
+                !ops->Minv &&
+                (cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED || cfg->mass_solver == SSE_MASS_DIAGONAL);
+      if (ok) {
+        const int H = n1 / 2;
+        std::vector<int> stride(d);
+        for (int l = 0; l < d; ++l) {
+          int st = 1;
+          for (int q = l + 1; q < d; ++q) st *= n1;
+          stride[l] = st;
+        }
+        // every non-zero of S_m must couple two nodes of one tensor line l with an allowed m
+        for (int m = 0; m < d && ok; ++m)
+          for (int i = 0; i < Nq && ok; ++i)
+            for (int j = 0; j < Nq && ok; ++j) {
+              if (S[m][(size_t)i * Nq + j] == 0.0) continue;
+              int line = -1, ndiff = 0;
+              for (int l = 0; l < d; ++l)
+                if ((i / stride[l]) % n1 != (j / stride[l]) % n1) { line = l; ++ndiff; }
+              if (ndiff != 1 || !(collapsed ? m >= line : m == line)) ok = false;
+            }
+        if (ok) {
+          std::vector<double> Sp((size_t)d * H * d * Nq, 0.0);
+          for (int l = 0; l < d; ++l)
+            for (int o = 1; o <= H; ++o)
+              for (int i = 0; i < Nq; ++i) {
+                int al = (i / stride[l]) % n1;
+                int ap = (al + o) % n1;
+                int j = i + (ap - al) * stride[l];
+                for (int m = 0; m < d; ++m)
+                  Sp[(((size_t)l * H + (o - 1)) * d + m) * Nq + i] = S[m][(size_t)i * Nq + j];
+              }
+          std::vector<int> Cj((size_t)kc * Nq), Rred(R.ci.size());
+          std::vector<double> Cvv((size_t)kc * Nq), Rvv((size_t)kc * Nq);
+          for (int i = 0; i < Nq; ++i)
+            for (int q = 0; q < kc; ++q) {
+              int en = Rt.rp[i] + q;
+              Cj[(size_t)q * Nq + i] = Rt.ci[en];
+              Cvv[(size_t)q * Nq + i] = Cv[en];
+              Rvv[(size_t)q * Nq + i] = Rt.v[en];
+            }
+          for (int j = 0; j < Nf; ++j)
+            for (int en = R.rp[j]; en < R.rp[j + 1]; ++en) {
+              int i = R.ci[en];
+              Rred[en] = (Rslot[en] - Rt.rp[i]) * Nq + i;
+            }
+          if (dev_upload_vec(h, Sp, &h->F.Sp) || dev_upload_vec(h, Cj, &h->F.Cj) ||
+              dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv) ||
+              dev_upload_vec(h, Rred, &h->F.Rred))
+            return -1;
+          h->fast_b = 1;
+          h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
+        }
+      }
     }
   }
   {
@@ -396,6 +528,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   // ---- geometry (kept in the reference's layout: every element block is contiguous)
   Geo& G = h->G;
   G.N_e = Ne;
+  G.k_begin = 0;
   {
     double *p1, *p2, *p3, *p4;
     if (dev_upload(h, geo->J_q, (size_t)Nq * Ne, &p1) ||
@@ -501,8 +634,39 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     *thr = std::max(64, std::min(256, t));
     return 0;
   };
-  if (pick(smem_a, &h->E_a, &h->thr_a, &h->smem_a)) return -1;
-  if (pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b)) return -1;
+  // specialised kernels, when this (dim, n1, law) combination is instantiated
+  {
+    const int n1 = ops->n1d;
+    size_t nd1 = 1;
+    for (int m = 0; m < d; ++m) nd1 *= (size_t)std::max(n1, 1);
+    const bool mass_ok = !ops->Minv && (cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED ||
+                                         cfg->mass_solver == SSE_MASS_DIAGONAL);
+    const bool force_generic = getenv("SSE_B200_GENERIC") != nullptr;
+    if (!force_generic && !h->second_order && cfg->strategy == SSE_REFERENCE_OPERATOR &&
+        (int)nd1 == Nq && mass_ok)
+      h->fast_a = fast_a_key(d, n1, law_t);
+    if (h->fast_b && !force_generic)
+      h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
+    else
+      h->fast_b = 0;
+  }
+  auto smem_a_fast = [&](int E) {
+    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf +
+                                         2 * (size_t)Nc * Nq);
+  };
+  auto smem_b_fast = [&](int E) {
+    const size_t H = (size_t)h->n1 / 2;
+    size_t sX = std::max(std::max(2 * H * Nc, (size_t)h->kc * Nc), (size_t)2 * Nc) * Nq;
+    return sizeof(double) * (size_t)E * ((size_t)NS * Nq + (size_t)d * d * Nq + (size_t)NS * Nf +
+                                         (size_t)d * Nf + (size_t)Nc * Nf + (size_t)Nc * Nq +
+                                         (size_t)Nc * Np + sX);
+  };
+  if (h->fast_a ? pick(smem_a_fast, &h->E_a, &h->thr_a, &h->smem_a)
+                : pick(smem_a, &h->E_a, &h->thr_a, &h->smem_a))
+    return -1;
+  if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
+                : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
+    return -1;
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -654,6 +818,46 @@ int sse_halo_unpack(sse_handle* h) {
   return 0;
 }
 
+int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end) {
+  if (!h) return fail("null handle");
+  if (k_begin < 0 || k_end > h->cfg.N_e || k_begin > k_end) return fail("bad element range");
+  if (k_begin == k_end) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  RK rk{};
+  h->G.k_begin = k_begin;
+  h->G.N_e = k_end;
+  int rc = run_b(h, dudt_dev ? dudt_dev : h->dudt, rk);
+  h->G.k_begin = 0;
+  h->G.N_e = h->cfg.N_e;
+  return rc;
+}
+
+int sse_set_stream(sse_handle* h, void* stream) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)stream;
+  h->own_stream = false;
+  return 0;
+}
+
+int sse_upload_state(sse_handle* h, const double* u_host) {
+  if (!h || !u_host) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->u, u_host, h->n_state * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int sse_download_dudt(sse_handle* h, double* dudt_host) {
+  if (!h || !dudt_host) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(dudt_host, h->dudt, h->n_state * sizeof(double), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int sse_sync(sse_handle* h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->cfg.device));
@@ -691,6 +895,51 @@ int sse_time_residual(sse_handle* h, int reps, int split, float* ms) {
       ms[2] += tb;
     }
   }
+  return 0;
+}
+
+// FP64 FMA-chain microbenchmark: the measured denominator for the FP64-bound kernels
+// (MEASURED_PEAKS.json carries no FP64 figure).
+__global__ void k_fp64_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int sse_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail("null argument");
+  CU(cudaSetDevice(device));
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double* out = nullptr;
+  CU(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(out, iters, 1.0);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
   return 0;
 }
 

@@ -58,7 +58,9 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_nodal_values", "sse_time_derivative", "sse_set_state", "sse_get_state",
            "sse_state_ptr", "sse_rk_stage", "sse_rk_step_ck54", "sse_halo_setup",
            "sse_halo_buffers", "sse_halo_pack", "sse_halo_unpack", "sse_sync", "sse_stream",
-           "sse_time_residual", "sse_kernel_launches", "sse_device_bytes"]
+           "sse_time_residual", "sse_kernel_launches", "sse_device_bytes",
+           "sse_measure_fp64_peak", "sse_time_derivative_range", "sse_set_stream",
+           "sse_upload_state", "sse_download_dudt"]
 
 
 def load_library(path: Optional[str] = None):
@@ -97,9 +99,23 @@ def load_library(path: Optional[str] = None):
     lib.sse_kernel_launches.restype = C.c_int64
     lib.sse_device_bytes.argtypes = [vp]
     lib.sse_device_bytes.restype = C.c_int64
+    lib.sse_measure_fp64_peak.argtypes = [C.c_int, c_d_p]
+    lib.sse_time_derivative_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    lib.sse_set_stream.argtypes = [vp, vp]
+    lib.sse_upload_state.argtypes = [vp, vp]
+    lib.sse_download_dudt.argtypes = [vp, vp]
     if path is None:
         _LIB = lib
     return lib
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of the device in TFLOP/s (library microbenchmark)."""
+    lib = load_library()
+    out = C.c_double()
+    if lib.sse_measure_fp64_peak(device, C.byref(out)) != 0:
+        raise RuntimeError("sse_measure_fp64_peak failed: " + lib.sse_last_error().decode())
+    return float(out.value)
 
 
 def _dp(a):
@@ -214,6 +230,8 @@ class DeviceResidual:
             Vd = _f64(V.to_dense())
             self._keep.append(Vd)
             ops.V_dense = _dp(Vd)
+        if ops.n1d == 0 and ra.D_1D is not None and len({D1.shape[0] for D1 in ra.D_1D}) == 1:
+            ops.n1d = ra.D_1D[0].shape[0]          # tensor-product element: nodes per direction
         rp, ci, val = ra.R.to_csr()
         self._keep += [rp, ci, val]
         ops.R_rowptr, ops.R_col, ops.R_val = _ip(rp), _ip(ci), _dp(val)
@@ -306,6 +324,21 @@ class DeviceResidual:
     def time_derivative(self, dudt_ptr: int = 0):
         self._check(self.lib.sse_time_derivative(self.h, dudt_ptr or None),
                     "sse_time_derivative")
+
+    def time_derivative_range(self, k_begin: int, k_end: int, dudt_ptr: int = 0):
+        self._check(self.lib.sse_time_derivative_range(self.h, dudt_ptr or None, k_begin, k_end),
+                    "sse_time_derivative_range")
+
+    def set_stream(self, stream: int):
+        self._check(self.lib.sse_set_stream(self.h, stream), "sse_set_stream")
+
+    def upload_state(self, u: np.ndarray):
+        assert u.shape == self.shape and u.dtype == np.float64 and u.flags.c_contiguous
+        self._check(self.lib.sse_upload_state(self.h, u.ctypes.data), "sse_upload_state")
+
+    def download_dudt(self, dudt: np.ndarray):
+        assert dudt.shape == self.shape and dudt.dtype == np.float64 and dudt.flags.c_contiguous
+        self._check(self.lib.sse_download_dudt(self.h, dudt.ctypes.data), "sse_download_dudt")
 
     def set_state(self, u: np.ndarray):
         u = _f64(u)

@@ -1,0 +1,228 @@
+"""Element-sharded multi-GPU residual: one process per GPU, facet-trace halo over NCCL.
+
+The reference has no distributed path at all (its only parallelism is ``Threads.@threads`` over
+elements, /root/reference/src/Solvers/Solvers.jl:498-518).  The only inter-element data the
+residual reads is the exterior trace ``u_f[CI[mapP[:, k]], :]``
+(flux_differencing_form.jl:312-313, standard_form_first_order.jl:33-34), so sharding the
+elements needs exactly one neighbour exchange of trace values between loop A and loop B:
+
+    loop A (all local elements)  ->  pack boundary traces  ->  isend/irecv (NCCL, NVLink)
+    loop B on interior elements (overlaps the transfer)    ->  unpack halo  ->  loop B on the
+    boundary elements.
+
+``partition`` is pure NumPy (tested on CPU with gloo, tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+
+@dataclass
+class Partition:
+    rank: int
+    world: int
+    start: int                   # first global element owned
+    stop: int                    # one past the last
+    mapP_local: np.ndarray       # (N_f, N_loc) local/halo linear indices
+    n_halo: int
+    send_idx: np.ndarray         # local linear indices (j + N_f*k_loc) to pack, grouped by peer
+    send_counts: Dict[int, int]  # peer -> number of trace nodes sent (ordered by peer rank)
+    recv_counts: Dict[int, int]  # peer -> number of trace nodes received (halo slots, in order)
+    interior: tuple              # (k_lo, k_hi): local elements that read no halo value
+
+    @property
+    def elements(self):
+        return np.arange(self.start, self.stop)
+
+
+def element_ranges(N_e: int, world: int):
+    """Equal-count contiguous chunks of the lexicographic element ordering."""
+    bounds = [(N_e * r) // world for r in range(world + 1)]
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def partition(mapP: np.ndarray, rank: int, world: int) -> Partition:
+    """Split the global connectivity ``mapP`` (N_f, N_e) for ``rank``.
+
+    Halo slots are numbered peer by peer (ascending peer rank) and, within a peer, by the
+    owner's global trace index; the owner packs its send list in the same order, so no index
+    lists ever have to be communicated."""
+    N_f, N_e = mapP.shape
+    ranges = element_ranges(N_e, world)
+    start, stop = ranges[rank]
+    n_loc = stop - start
+    starts = np.array([r[0] for r in ranges] + [N_e])
+    tgt = mapP[:, start:stop]                                # global linear index j' + N_f*k'
+    tk = tgt // N_f
+    owner = np.searchsorted(starts, tk, side="right") - 1
+    local = owner == rank
+    mp = np.empty_like(tgt)
+    mp[local] = tgt[local] - N_f * start
+    send_idx: List[np.ndarray] = []
+    send_counts: Dict[int, int] = {}
+    recv_counts: Dict[int, int] = {}
+    halo_off = 0
+    gl = (np.arange(N_f)[:, None] + N_f * (start + np.arange(n_loc))[None, :])   # own global idx
+    ll = (np.arange(N_f)[:, None] + N_f * np.arange(n_loc)[None, :])            # own local idx
+    for peer in range(world):
+        if peer == rank:
+            continue
+        sel = owner == peer
+        cnt = int(sel.sum())
+        if cnt == 0:
+            continue
+        # receive: order halo slots by the owner's global index
+        want = tgt[sel]
+        order = np.argsort(want, kind="stable")
+        slot = np.empty(cnt, dtype=np.int64)
+        slot[order] = halo_off + np.arange(cnt)
+        mp[sel] = N_f * n_loc + slot
+        recv_counts[peer] = cnt
+        halo_off += cnt
+        # send: my nodes whose partner lives on `peer`, ordered by my global index
+        mine_g = gl[sel]
+        o2 = np.argsort(mine_g, kind="stable")
+        send_idx.append(ll[sel][o2])
+        send_counts[peer] = cnt
+    touches_halo = np.any(~local, axis=0)
+    inner = np.nonzero(~touches_halo)[0]
+    if len(inner) == 0:
+        interior = (0, 0)
+    else:
+        # largest contiguous run of elements that read no halo value
+        brk = np.nonzero(np.diff(inner) > 1)[0]
+        seg_s = np.concatenate(([0], brk + 1))
+        seg_e = np.concatenate((brk + 1, [len(inner)]))
+        best = int(np.argmax(seg_e - seg_s))
+        interior = (int(inner[seg_s[best]]), int(inner[seg_e[best] - 1]) + 1)
+    return Partition(rank, world, start, stop, mp, halo_off,
+                     np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int64),
+                     send_counts, recv_counts, interior)
+
+
+class _DevBuf:
+    """Expose a raw device pointer through __cuda_array_interface__ (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class DistributedResidual:
+    """Residual of one element shard on one GPU (world = 1: the whole mesh, no exchange)."""
+
+    def __init__(self, solver, rank: int = 0, world: int = 1, device: int = 0):
+        from .device import DeviceResidual
+        self.solver, self.rank, self.world = solver, rank, world
+        sd = solver.spatial_discretization
+        N_f = sd.reference_approximation.N_f
+        if world == 1:
+            self.part = None
+            self.elements = np.arange(sd.N_e)
+            self.dev = DeviceResidual(solver, device=device)
+        else:
+            import torch
+            self.torch = torch
+            self.part = partition(sd.mesh.mapP, rank, world)
+            self.elements = self.part.elements
+            self.dev = DeviceResidual(solver, device=device, mapP=self.part.mapP_local,
+                                      n_halo=self.part.n_halo, elements=self.elements)
+            self.dev.halo_setup(self.part.send_idx)
+            s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
+            N_c = self.dev.N_c
+            dv = torch.device("cuda", device)
+            self.send_t = torch.as_tensor(_DevBuf(s_ptr, n_s * N_c), device=dv)
+            self.recv_t = torch.as_tensor(_DevBuf(r_ptr, n_r * N_c), device=dv)
+            # run the library on torch's current stream so NCCL ordering is stream-ordered
+            self.dev.set_stream(torch.cuda.current_stream(dv).cuda_stream)
+            self._ops = None
+        self.local_shape = self.dev.shape
+        self.n_local_state = int(np.prod(self.local_shape))
+
+    # ------------------------------------------------------------------ plumbing
+    def _p2p_ops(self):
+        import torch.distributed as dist
+        ops, so, ro = [], 0, 0
+        N_c = self.dev.N_c
+        for peer in sorted(set(self.part.send_counts) | set(self.part.recv_counts)):
+            ns = self.part.send_counts.get(peer, 0) * N_c
+            nr = self.part.recv_counts.get(peer, 0) * N_c
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, self.recv_t[ro:ro + nr], peer))
+            if ns:
+                ops.append(dist.P2POp(dist.isend, self.send_t[so:so + ns], peer))
+            so += ns
+            ro += nr
+        return ops
+
+    def _exchange_and_time_derivative(self):
+        import torch.distributed as dist
+        d = self.dev
+        d.halo_pack()
+        works = dist.batch_isend_irecv(self._p2p_ops())
+        k_lo, k_hi = self.part.interior
+        if k_hi > k_lo:
+            d.time_derivative_range(k_lo, k_hi)        # overlaps the NVLink transfer
+        for w in works:
+            w.wait()
+        d.halo_unpack()
+        if k_lo > 0:
+            d.time_derivative_range(0, k_lo)
+        if k_hi < d.N_e:
+            d.time_derivative_range(max(k_hi, k_lo), d.N_e)
+
+    def residual(self):
+        """One residual of the device-resident state (dudt stays on the device)."""
+        if self.world == 1:
+            self.dev.nodal_values()
+            self.dev.time_derivative()
+        else:
+            self.dev.nodal_values()
+            self._exchange_and_time_derivative()
+
+    def residual_host(self, u: np.ndarray, dudt: np.ndarray):
+        """Public-API path with host buffers for this shard (H2D + residual + D2H)."""
+        if self.world == 1:
+            self.dev.residual_host(u, dudt)
+            return
+        self.dev.upload_state(u)
+        self.residual()
+        self.dev.download_dudt(dudt)
+
+    def timed_residuals(self, steps: int) -> float:
+        """Milliseconds for ``steps`` residuals, CUDA events on the launching stream."""
+        if self.world == 1:
+            return self.dev.time_residual(steps, split=False)[0]
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.residual()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def split_times(self, reps: int):
+        _, ta, tb = self.dev.time_residual(reps, split=True)
+        return {"loop_a_ms": ta / reps, "loop_b_ms": tb / reps, "note":
+                "per-kernel CUDA-event times from a separate pass (halo exchange excluded)"}
+
+    def set_state(self, u_local: np.ndarray):
+        self.dev.set_state(u_local)
+
+    def get_dudt(self) -> np.ndarray:
+        out = np.empty(self.local_shape)
+        self.dev.download_dudt(out)
+        return out
+
+    def kernel_launches(self) -> int:
+        return self.dev.kernel_launches()
+
+    def sync(self):
+        self.dev.sync()
+
+    def close(self):
+        self.dev.close()

@@ -185,7 +185,7 @@ def build_face_connectivity(elem, VXYZ, EToV, limits, fv):
     return FToF
 
 
-def build_mapP(xyzf, FToF, nfaces, limits, tol=1e-8, chunk=20000):
+def build_mapP(xyzf, FToF, nfaces, limits, tol=1e-7, chunk=65536):
     """Facet-node permutation between glued faces by (periodic) coordinate matching."""
     d = len(xyzf)
     N_f, N_e = xyzf[0].shape
@@ -202,12 +202,21 @@ def build_mapP(xyzf, FToF, nfaces, limits, tol=1e-8, chunk=20000):
         e = min(s + chunk, N_e * nfaces)
         A = X[s:e]                                            # (C, npf, d)
         Bn = X[pidx[s:e]]
-        dlt = _periodic_diff(A[:, :, None, :], Bn[:, None, :, :], L)
-        dist = np.einsum("cabm,cabm->cab", dlt, dlt)
+        # shift the partner face by whole periods so the two faces coincide
+        shift = np.rint((A.mean(axis=1) - Bn.mean(axis=1)) / L) * L
+        Bn = Bn + shift[:, None, :]
+        # |a-b|^2 = |a|^2 + |b|^2 - 2 a.b  (centred to keep round-off small)
+        c0 = A.mean(axis=1, keepdims=True)
+        Ac, Bc = A - c0, Bn - c0
+        dist = (np.einsum("cam,cam->ca", Ac, Ac)[:, :, None]
+                + np.einsum("cbm,cbm->cb", Bc, Bc)[:, None, :]
+                - 2.0 * np.matmul(Ac, Bc.transpose(0, 2, 1)))
         arg = np.argmin(dist, axis=2)
         best = np.take_along_axis(dist, arg[:, :, None], axis=2)[:, :, 0]
         if np.max(best) > (tol * scale) ** 2:
             raise RuntimeError(f"facet nodes do not conform (max dist {np.sqrt(np.max(best)):.3e})")
+        if npf > 1 and np.any(np.sort(arg, axis=1) != np.arange(npf)[None, :]):
+            raise RuntimeError("facet node matching is not a permutation")
         mapP[s:e] = arg + (pf[s:e] * npf)[:, None] + (pk[s:e] * N_f)[:, None]
     # back to (N_f, N_e)
     return np.ascontiguousarray(mapP.reshape(N_e, nfaces * npf).T)

@@ -163,10 +163,16 @@ def project_function(initial_data, sd: SpatialDiscretization) -> np.ndarray:
     if isinstance(ra.V, IdentityMap):
         return u_q
     V = ra.V.to_dense()
-    WJ = ra.W[None, :] * sd.geometric_factors.J_q
-    M = np.einsum("qa,kq,qb->kab", V, WJ, V)
-    rhs = np.einsum("qp,kq,keq->kpe", V, WJ, u_q)
-    return np.ascontiguousarray(np.linalg.solve(M, rhs).transpose(0, 2, 1))
+    J_q = sd.geometric_factors.J_q
+    u0 = np.empty((sd.N_e, u_q.shape[1], ra.N_p))
+    chunk = 32768
+    for s in range(0, sd.N_e, chunk):
+        e = min(s + chunk, sd.N_e)
+        VW = V.T[None, :, :] * (ra.W[None, :] * J_q[s:e])[:, None, :]   # (C, N_p, N_q)
+        M = VW @ V
+        rhs = VW @ u_q[s:e].transpose(0, 2, 1)                          # (C, N_p, N_c)
+        u0[s:e] = np.linalg.solve(M, rhs).transpose(0, 2, 1)
+    return u0
 
 
 initialize = project_function
