@@ -27,7 +27,10 @@ def run(M=6, warp=True, steps=3, warmup=1):
     dof = u0.size
     try:
         import c_oracle
-        fn, cores, impl = c_oracle.make_residual(prob), c_oracle.num_threads(), "C/OpenMP"
+        V = solver.spatial_discretization.reference_approximation.V
+        warped = (V.A, V.B, getattr(V, "C", None), V.sigma_i) if hasattr(V, "sigma_i") else None
+        fn, cores, impl = (c_oracle.make_residual(prob, warped), c_oracle.num_threads(),
+                           "C/OpenMP")
     except Exception:
         fn, cores, impl = (lambda u: oc.semi_discrete_residual(prob, u)), 1, "NumPy"
     for _ in range(warmup):

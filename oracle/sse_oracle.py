@@ -350,15 +350,13 @@ def facet_correction(prob, C, r_q, f_f, u_q, u_f):
     return r_q, f_f
 
 
-def residual_fluxdiff(prob, u):
-    """Solvers.jl:476-518 with flux_differencing_form.jl:268-347."""
+def fluxdiff_loop_b(prob, u_q, u_f, u_out):
+    """time_derivative! (flux_differencing_form.jl:294-347) given the exterior traces u_out."""
     law, form = prob["law"], prob["form"]
     V, R = prob["V"], prob["R"]
     S, C = prob.get("_SC") or flux_differencing_operators(prob)
     prob["_SC"] = (S, C)
     n_f, BJf = _facet_geometry(prob)
-    u_q, u_f = nodal_values_fluxdiff(prob, u)
-    u_out = _gather_exterior(u_f, prob["mapP"])
     f_f = numerical_flux(law, form["inviscid"], u_f, u_out, n_f, form["two_point"])
     f_f = f_f * BJf[:, :, None]
     r_q = flux_difference(prob, S, u_q)
@@ -366,6 +364,13 @@ def residual_fluxdiff(prob, u):
     r_q = r_q - np.einsum("fq,kfe->kqe", R, f_f)
     dudt = np.einsum("qp,kqe->kep", V, r_q)
     return mass_matrix_solve(prob, dudt)
+
+
+def residual_fluxdiff(prob, u):
+    """Solvers.jl:476-518 with flux_differencing_form.jl:268-347: loop A, (barrier), loop B."""
+    u_q, u_f = nodal_values_fluxdiff(prob, u)
+    u_out = _gather_exterior(u_f, prob["mapP"])
+    return fluxdiff_loop_b(prob, u_q, u_f, u_out)
 
 
 # ================================================= standard form, reference operators

@@ -17,10 +17,11 @@ namespace sse {
 
 struct FastTables {
   const double* Sp;    // [DIM][H][DIM][NQ]: S_m[i, partner(i; l, o)]
-  const int* Cj;       // [KC][NQ] facet node of ELL slot k
+  const int* Cj;       // [KC][NQ] facet node of ELL slot k | (face index << 16)
   const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
   const double* Rv;    // [KC][NQ] R[j, i]
-  const int* Rred;     // per R-CSR entry: k * NQ + i  (slot of the facet-correction term)
+  const int* Rred;     // per R-CSR entry (rows sorted by slot): (k mod KH)*NC*(E*NQ) + i
+  const int* Rmid;     // [N_f] first entry of row j whose slot k >= ceil(KC/2)
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -394,9 +395,11 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 
 // ==================================================== loop B, flux-differencing form
 // shared (doubles): sS[NS][E*NQ] | sL[DD][E*NQ] | sSf[NS][E*NF] | sNf[DIM][E*NF] |
-//                   sFf[E][NC][NF] | sR[E][NC][NQ] | sM[E][NC][NP] | sX[max(2*H*NC, KC*NC, 2*NC)*E*NQ]
+//                   sFf[E][NC][NF] | sR[E][NC][NQ] | sM[E][NC][NP] | sX[max(2*H, KH, 2)*NC*E*NQ]
+// KH = ceil(KC/2): the facet-correction terms are exchanged in two halves to keep the
+// per-element footprint at ~52 KB (4 CTAs of 128 threads per SM for Tet p=4).
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)
 k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt, int E) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
@@ -404,6 +407,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   constexpr int NQ = ipow(N1, DIM);
   constexpr int DD = DIM * DIM;
   constexpr int H = N1 / 2;
+  constexpr int KH = (KC + 1) / 2;
   extern __shared__ double sm[];
   const int Np = T.N_p, Nf = T.N_f;
   const int nq = E * NQ, nf = E * Nf;
@@ -431,14 +435,13 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     double uu[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) uu[c] = u_q[(k * NC + c) * NQ + i];
+#pragma unroll
+    for (int c = 0; c < DD; ++c) Li[c] = G.L_q[(k * DD + c) * NQ + i];
     cons_to_state<DIM, LAW>(P, uu, si);
 #pragma unroll
     for (int c = 0; c < NS; ++c) sS[c * nq + tid] = si[c];
 #pragma unroll
-    for (int c = 0; c < DD; ++c) {
-      Li[c] = G.L_q[(k * DD + c) * NQ + i];
-      sL[c * nq + tid] = Li[c];
-    }
+    for (int c = 0; c < DD; ++c) sL[c * nq + tid] = Li[c];
   }
   // ---- phase 1: interface numerical flux at the facet nodes
   SSE_LOOP(idx, nf) {
@@ -446,14 +449,15 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     long long k = min(k0 + ee, G.N_e - 1);
     long long gj = k * Nf + j;
     double nJ[DIM], nfv[DIM], sl[NS], fs[NC];
-    double iJf = __drcp_rn(G.J_f[gj]);
+    const double Jf = G.J_f[gj];
+    const int ext = G.toff[gj];
 #pragma unroll
-    for (int m = 0; m < DIM; ++m) {
-      nJ[m] = G.nJf[gj * DIM + m];
-      nfv[m] = nJ[m] * iJf;
-    }
-    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * Nf + j, G.toff[gj], Nf, nfv, sl, fs);
-    double bj = __ldg(T.B + j) * G.J_f[gj];
+    for (int m = 0; m < DIM; ++m) nJ[m] = G.nJf[gj * DIM + m];
+    const double iJf = frcp(Jf);
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
+    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * Nf + j, ext, Nf, nfv, sl, fs);
+    double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
     for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * Nf + j] = bj * fs[c];
 #pragma unroll
@@ -466,34 +470,36 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phase 2: volume flux differencing, every pair on a tensor line evaluated once
 #pragma unroll
   for (int l = 0; l < DIM; ++l) {
-    constexpr int dummy = 0;
-    (void)dummy;
     const int stride = (l == 0) ? ipow(N1, DIM - 1) : (l == 1 ? ipow(N1, DIM - 2) : 1);
     const int al = (i / stride) % N1;
     double* buf = sX + (l & 1) * (H * NC * nq);
     if (active) {
-#pragma unroll
+#pragma unroll 1
       for (int o = 1; o <= H; ++o) {
         const bool mine = (2 * o < N1) || (al < N1 / 2);
         if (mine) {
           int ap = al + o;
           if (ap >= N1) ap -= N1;
           const int jt = tid + (ap - al) * stride;
-          double cv[DIM], sj[NS], f[NC];
+          const double* Sp = F.Sp + ((l * H + (o - 1)) * DIM) * NQ + i;
+          double sv[DIM], cv[DIM], sj[NS], f[NC];
+#pragma unroll
+          for (int m = 0; m < DIM; ++m) {
+            const bool used = COLLAPSED ? (m >= l) : (m == l);
+            sv[m] = used ? __ldg(Sp + m * NQ) : 0.0;
+          }
+#pragma unroll
+          for (int c = 0; c < NS; ++c) sj[c] = sS[c * nq + jt];
 #pragma unroll
           for (int n = 0; n < DIM; ++n) {
             double acc = 0.0;
 #pragma unroll
             for (int m = 0; m < DIM; ++m) {
               const bool used = COLLAPSED ? (m >= l) : (m == l);
-              if (used)
-                acc = fma(__ldg(F.Sp + ((l * H + (o - 1)) * DIM + m) * NQ + i),
-                          Li[m + DIM * n] + sL[(m + DIM * n) * nq + jt], acc);
+              if (used) acc = fma(sv[m], Li[m + DIM * n] + sL[(m + DIM * n) * nq + jt], acc);
             }
             cv[n] = acc;
           }
-#pragma unroll
-          for (int c = 0; c < NS; ++c) sj[c] = sS[c * nq + jt];
           two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, cv, f);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
@@ -518,55 +524,63 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
       }
     }
   }
-  __syncthreads();   // all reads of the pair buffers are done before sX is reused
 
-  // ---- phase 3: facet correction (ELL rows of C = R^T B)
-  if (active && !T.r_is_selection) {
+  // ---- phases 3/4: facet correction (ELL rows of C = R^T B), exchanged in two halves
+  if (!T.r_is_selection) {
 #pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      const int j = __ldg(F.Cj + kk * NQ + i);
-      const double cij = __ldg(F.Cv + kk * NQ + i);
-      const int fc = j / T.npf;
-      const int jj = e * Nf + j;
-      double nJ[DIM], sj[NS], f[NC];
+    for (int half = 0; half < 2; ++half) {
+      __syncthreads();   // previous users of sX (pair buffers / first half) are done
+      if (active) {
+#pragma unroll 1
+        for (int kk = half * KH; kk < (half == 0 ? KH : KC); ++kk) {
+          const int jp = __ldg(F.Cj + kk * NQ + i);      // facet node | face << 16
+          const double cij = __ldg(F.Cv + kk * NQ + i);
+          const int j = jp & 0xffff, fc = jp >> 16;
+          const int jj = e * Nf + j;
+          double nJ[DIM], sj[NS], f[NC];
 #pragma unroll
-      for (int n = 0; n < DIM; ++n) {
-        double acc = 0.0;
+          for (int c = 0; c < NS; ++c) sj[c] = sSf[c * nf + jj];
 #pragma unroll
-        for (int m = 0; m < DIM; ++m) acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
-        nJ[n] = fma(0.5, acc, sNf[n * nf + jj]);
+          for (int n = 0; n < DIM; ++n) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < DIM; ++m)
+              acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
+            nJ[n] = fma(0.5, acc, sNf[n * nf + jj]);
+          }
+          two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            double dlt = cij * f[c];
+            r[c] -= dlt;
+            sX[((kk - half * KH) * NC + c) * nq + tid] = dlt;
+          }
+        }
       }
-#pragma unroll
-      for (int c = 0; c < NS; ++c) sj[c] = sSf[c * nf + jj];
-      two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        double dlt = cij * f[c];
-        r[c] -= dlt;
-        sX[(kk * NC + c) * nq + tid] = dlt;
+      __syncthreads();
+      // f_f -= column sums of this half's terms (R rows sorted by slot, split at Rmid);
+      // Rred holds the ready-made shared-memory offset kk_local*NC*nq + i of each term
+      SSE_LOOP(idx, NC * nf) {
+        const int c = idx % NC, ej = idx / NC;
+        const int j = ej % Nf, ee = ej / Nf;
+        const int b = half == 0 ? __ldg(T.R_rp + j) : __ldg(F.Rmid + j);
+        const int en = half == 0 ? __ldg(F.Rmid + j) : __ldg(T.R_rp + j + 1);
+        if (en > b) {
+          const double* base = sX + c * nq + ee * NQ;
+          double acc = 0.0;
+#pragma unroll 5
+          for (int q = b; q < en; ++q) acc += base[__ldg(F.Rred + q)];
+          sFf[(ee * NC + c) * Nf + j] -= acc;
+        }
       }
     }
   }
   __syncthreads();
-  // ---- phase 4: f_f -= column sums of the facet-correction terms
-  if (!T.r_is_selection) {
-    SSE_LOOP(idx, NC * nf) {
-      int j = idx % Nf, c = (idx / Nf) % NC, ee = idx / (Nf * NC);
-      double acc = 0.0;
-      const int b = __ldg(T.R_rp + j), en = __ldg(T.R_rp + j + 1);
-      for (int q = b; q < en; ++q) {
-        int pk = __ldg(F.Rred + q);
-        acc += sX[((pk / NQ) * NC + c) * nq + ee * NQ + (pk % NQ)];
-      }
-      sFf[idx] -= acc;
-    }
-    __syncthreads();
-  }
   // ---- phase 5: r_q -= R^T f_f (ELL), then hand r_q to the modal projection
   if (active) {
-#pragma unroll
+#pragma unroll 1
     for (int kk = 0; kk < KC; ++kk) {
-      const int j = __ldg(F.Cj + kk * NQ + i);
+      const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
       const double rv = __ldg(F.Rv + kk * NQ + i);
 #pragma unroll
       for (int c = 0; c < NC; ++c) r[c] = fma(-rv, sFf[(e * NC + c) * Nf + j], r[c]);

@@ -30,9 +30,18 @@ template <int DIM, int LAW> struct LawTraits {
   static constexpr int NS = (LAW == LAW_EULER) ? DIM + 3 : 1;
 };
 
-// a / b through the correctly rounded reciprocal (MUFU.RCP64H + Newton steps, no slow path):
-// <= 1 ulp from IEEE division, far inside the 1e-12 parity budget.
-__device__ __forceinline__ double fdiv(double a, double b) { return a * __drcp_rn(b); }
+// a / b = a * frcp(b): ~1 ulp from IEEE division, far inside the 1e-12 parity budget.
+// frcp: MUFU.RCP64H seed (rel. error < 2^-22) + two Newton steps; branch-free.  Valid for the
+// normal, finite, non-zero arguments that occur here (densities, pressures, Jacobians).
+__device__ __forceinline__ double frcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b); }
 
 // logmean / inv_logmean (ConservationLaws.jl:132-156).  With q = (x-y)^2, t = (x+y)^2 the
 // reference's f^2 equals q/t and its Taylor branch (x+y)*105/(210 + f2(70 + f2(42 + 30 f2)))
@@ -70,7 +79,7 @@ template <int DIM, int LAW>
 __device__ __forceinline__ void cons_to_state(const Phys& P, const double* u, double* s) {
   if constexpr (LAW == LAW_EULER) {
     double rho = u[0];
-    double irho = __drcp_rn(rho);
+    double irho = frcp(rho);
     double k = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) {
@@ -206,7 +215,7 @@ __device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, 
     for (int m = 0; m < DIM; ++m) k += u[1 + m] * u[1 + m];
     k *= 0.5 / u[0];
     double p = gm1 * (u[DIM + 1] - k);
-    double inv_p = __drcp_rn(p);
+    double inv_p = frcp(p);
     // log(p / rho^gamma) = log p - gamma log rho (two logs instead of pow + log)
     w[0] = (g - (log(p) - g * log(u[0]))) / gm1 - k * inv_p;
 #pragma unroll

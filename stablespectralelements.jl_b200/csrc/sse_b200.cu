@@ -67,6 +67,7 @@ struct sse_handle {
   // compile-time specialised tensor-product path
   FastTables F{};
   int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
+  std::vector<int> rred_pk;
 };
 
 template <typename Tp>
@@ -492,20 +493,33 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
           for (int i = 0; i < Nq; ++i)
             for (int q = 0; q < kc; ++q) {
               int en = Rt.rp[i] + q;
-              Cj[(size_t)q * Nq + i] = Rt.ci[en];
+              Cj[(size_t)q * Nq + i] = Rt.ci[en] | ((Rt.ci[en] / T.npf) << 16);
               Cvv[(size_t)q * Nq + i] = Cv[en];
               Rvv[(size_t)q * Nq + i] = Rt.v[en];
             }
-          for (int j = 0; j < Nf; ++j)
+          std::vector<int> Rmid(Nf);
+          const int KH = (kc + 1) / 2;
+          for (int j = 0; j < Nf; ++j) {
+            std::vector<int> row;
             for (int en = R.rp[j]; en < R.rp[j + 1]; ++en) {
               int i = R.ci[en];
-              Rred[en] = (Rslot[en] - Rt.rp[i]) * Nq + i;
+              row.push_back((Rslot[en] - Rt.rp[i]) * Nq + i);
             }
-          if (dev_upload_vec(h, Sp, &h->F.Sp) || dev_upload_vec(h, Cj, &h->F.Cj) ||
-              dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv) ||
-              dev_upload_vec(h, Rred, &h->F.Rred))
+            std::sort(row.begin(), row.end());          // by slot k, then node
+            int mid = R.rp[j + 1];
+            for (size_t q = 0; q < row.size(); ++q) {
+              Rred[R.rp[j] + q] = row[q];
+              if (row[q] / Nq >= KH && mid == R.rp[j + 1]) mid = R.rp[j] + (int)q;
+            }
+            Rmid[j] = mid;
+          }
+          if (Nf >= 65536) ok = false;
+          if (ok && (dev_upload_vec(h, Sp, &h->F.Sp) || dev_upload_vec(h, Cj, &h->F.Cj) ||
+                     dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv) ||
+                     dev_upload_vec(h, Rmid, &h->F.Rmid)))
             return -1;
-          h->fast_b = 1;
+          h->rred_pk = Rred;   // turned into shared-memory offsets once E is known
+          h->fast_b = ok ? 1 : 0;
           h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
         }
       }
@@ -656,7 +670,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   };
   auto smem_b_fast = [&](int E) {
     const size_t H = (size_t)h->n1 / 2;
-    size_t sX = std::max(std::max(2 * H * Nc, (size_t)h->kc * Nc), (size_t)2 * Nc) * Nq;
+    size_t sX = std::max(std::max(2 * H * Nc, (size_t)((h->kc + 1) / 2) * Nc), (size_t)2 * Nc) * Nq;
     return sizeof(double) * (size_t)E * ((size_t)NS * Nq + (size_t)d * d * Nq + (size_t)NS * Nf +
                                          (size_t)d * Nf + (size_t)Nc * Nf + (size_t)Nc * Nq +
                                          (size_t)Nc * Np + sX);
@@ -667,6 +681,16 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
+  if (h->fast_b) {
+    const int KH = (h->kc + 1) / 2;
+    std::vector<int> off(h->rred_pk.size());
+    for (size_t q = 0; q < off.size(); ++q) {
+      int k = h->rred_pk[q] / Nq, i = h->rred_pk[q] % Nq;
+      int kl = k >= KH ? k - KH : k;
+      off[q] = kl * Nc * (h->E_b * Nq) + i;
+    }
+    if (dev_upload_vec(h, off, &h->F.Rred)) return -1;
+  }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
