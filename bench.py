@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--M", type=int, default=44, help="cubes per direction (6 M^3 tetrahedra)")
     ap.add_argument("--straight", action="store_true", help="straight-sided mesh (default: warped)")
-    ap.add_argument("--cpu-m", type=int, default=6, help="mesh size of the CPU baseline sample")
+    ap.add_argument("--cpu-m", type=int, default=16, help="mesh size of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
