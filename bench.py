@@ -90,9 +90,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(M, warp, lazy=True):
+def build_problem(M, warp, lazy=True, shard=None):
     import cases
-    return cases.euler_tet_case(p=4, M=M, lazy=lazy, warp=warp, interface="lf", ic="tgv")
+    return cases.euler_tet_case(p=4, M=M, lazy=lazy, warp=warp, interface="lf", ic="tgv",
+                                shard=shard)
 
 
 def cpu_reference_arm(args):
@@ -156,11 +157,15 @@ def main():
     from sse_b200.distributed import DistributedResidual
 
     t_setup = time.time()
-    solver, u0 = build_problem(args.M, warp=not args.straight, lazy=True)
-    N_e, N_c, N_p = u0.shape
+    # every rank builds the (cheap) global connectivity but only its own shard's geometry
+    solver, u0 = build_problem(args.M, warp=not args.straight, lazy=True,
+                               shard=(rank, world) if world > 1 else None)
+    N_e = solver.spatial_discretization.mesh.mapP.shape[1]
+    N_c, N_p = u0.shape[1], u0.shape[2]
     dof = N_e * N_c * N_p
     dres = DistributedResidual(solver, rank=rank, world=world, device=local_rank)
-    dres.set_state(u0[dres.elements])
+    u0_local = u0 if world > 1 else u0[dres.elements]
+    dres.set_state(u0_local)
     t_setup = time.time() - t_setup
 
     def barrier():
@@ -200,7 +205,7 @@ def main():
         du_host = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
         u_np = u_host.numpy().reshape(dres.local_shape)
         du_np = du_host.numpy().reshape(dres.local_shape)
-        u_np[...] = u0[dres.elements]
+        u_np[...] = u0_local
         ke = max(3, min(args.steps, 10))
         for _ in range(2):
             dres.residual_host(u_np, du_np)

@@ -399,8 +399,8 @@ __device__ __forceinline__ void interface_flux(const Phys& P, int two_point,
   double um[NC], up[NC], sr[NS];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    um[c] = u_f[own + (long long)c * stride];
-    up[c] = u_f[ext + (long long)c * stride];
+    um[c] = __ldcg(u_f + own + (long long)c * stride);
+    up[c] = __ldcg(u_f + ext + (long long)c * stride);
   }
   cons_to_state<DIM, LAW>(P, um, sl);
   cons_to_state<DIM, LAW>(P, up, sr);

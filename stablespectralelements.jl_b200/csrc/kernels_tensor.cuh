@@ -394,74 +394,108 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 }
 
 // ==================================================== loop B, flux-differencing form
-// shared (doubles): sS[NS][E*NQ] | sL[DD][E*NQ] | sSf[NS][E*NF] | sNf[DIM][E*NF] |
-//                   sFf[E][NC][NF] | sR[E][NC][NQ] | sM[E][NC][NP] | sX[max(2*H, KH, 2)*NC*E*NQ]
-// KH = ceil(KC/2): the facet-correction terms are exchanged in two halves to keep the
-// per-element footprint at ~52 KB (4 CTAs of 128 threads per SM for Tet p=4).
+// Compile-time geometry of the specialised loop-B kernel: EL elements per 128-thread CTA,
+// NF facet nodes, and the shared-memory carve-up (in doubles; regions holding double2 start
+// on even offsets).
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+struct FDCfg {
+  static constexpr int NC = LawTraits<DIM, LAW>::NC;
+  static constexpr int NS = LawTraits<DIM, LAW>::NS;
+  static constexpr int NS2 = (NS + 1) / 2;
+  static constexpr int NQ = ipow(N1, DIM);
+  static constexpr int EL = (128 / NQ) > 0 ? 128 / NQ : 1;
+  static constexpr int NF = COLLAPSED ? (DIM == 3 ? 4 * N1 * N1 : 3 * N1)
+                                      : 2 * DIM * ipow(N1, DIM - 1);
+  static constexpr int H = N1 / 2;
+  static constexpr int KH = (KC + 1) / 2;
+  static constexpr int nq = EL * NQ, nf = EL * NF;
+  static __host__ __device__ constexpr int ev(int n) { return (n + 1) & ~1; }
+  static constexpr int oS = 0;                                   // double2 [NS2][nq]
+  static constexpr int oLa = oS + 2 * NS2 * nq;                  // double2 [DIM][nq]
+  static constexpr int oLb = oLa + 2 * DIM * nq;                 // double  [DIM][nq] (3-D)
+  static constexpr int oSf = oLb + ev(DIM == 3 ? DIM * nq : 0);  // double2 [NS2][nf]
+  static constexpr int oNf = oSf + 2 * NS2 * nf;                 // double  [DIM][nf]
+  static constexpr int oFf = oNf + ev(DIM * nf);                 // double  [EL][NC][NF]
+  // r_q and the modal result alias the state/metric staging area, which is dead by then
+  static constexpr int oR = 0;                                   // double  [EL][NC][NQ]
+  static constexpr int oM = oR + ev(NC * nq);                    // double  [EL][NC][Np]
+  static constexpr int oEnd = oFf + ev(NC * nf);
+  static __host__ __device__ constexpr int xmax(int a, int b) { return a > b ? a : b; }
+  static constexpr int sX = xmax(xmax(2 * H * NC, KH * NC), 2 * NC) * nq;
+  static __host__ __device__ constexpr int oX(int Np) {
+    return xmax(oEnd, oM + ev(EL * NC * Np));
+  }
+  static __host__ __device__ constexpr size_t bytes(int Np) { return sizeof(double) * (size_t)(oX(Np) + sX); }
+};
+
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
 __global__ void __launch_bounds__(128, 4)
 k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
-                  const double* __restrict__ u_f, double* __restrict__ dudt, int E) {
-  constexpr int NC = LawTraits<DIM, LAW>::NC;
-  constexpr int NS = LawTraits<DIM, LAW>::NS;
-  constexpr int NQ = ipow(N1, DIM);
-  constexpr int DD = DIM * DIM;
-  constexpr int H = N1 / 2;
-  constexpr int KH = (KC + 1) / 2;
-  extern __shared__ double sm[];
-  const int Np = T.N_p, Nf = T.N_f;
-  const int nq = E * NQ, nf = E * Nf;
-  double* sS = sm;
-  double* sL = sS + NS * nq;
-  double* sSf = sL + DD * nq;
-  double* sNf = sSf + NS * nf;
-  double* sFf = sNf + DIM * nf;
-  double* sR = sFf + NC * nf;
-  double* sM = sR + NC * nq;
-  double* sX = sM + E * NC * Np;
-  const long long k0 = G.k_begin + (long long)blockIdx.x * E;
+                  const double* __restrict__ u_f, double* __restrict__ dudt) {
+  using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
+  constexpr int NC = Cf::NC, NS2 = Cf::NS2, NQ = Cf::NQ, NF = Cf::NF;
+  constexpr int DD = DIM * DIM, H = Cf::H, KH = Cf::KH, EL = Cf::EL, nq = Cf::nq, nf = Cf::nf;
+  extern __shared__ __align__(16) double sm[];
+  const int Np = T.N_p;
+  double2* sS2 = reinterpret_cast<double2*>(sm + Cf::oS);
+  double2* sLa = reinterpret_cast<double2*>(sm + Cf::oLa);
+  double* sLb = sm + Cf::oLb;
+  double2* sSf2 = reinterpret_cast<double2*>(sm + Cf::oSf);
+  double* sNf = sm + Cf::oNf;
+  double* sFf = sm + Cf::oFf;
+  double* sR = sm + Cf::oR;
+  double* sM = sm + Cf::oM;
+  double* sX = sm + Cf::oX(Np);
+  const long long k0 = G.k_begin + (long long)blockIdx.x * EL;
   const int tid = threadIdx.x;
   const bool active = tid < nq;
   const int e = active ? tid / NQ : 0;
   const int i = active ? tid % NQ : 0;
 
-  double si[NS], Li[DD], r[NC];
+  double si[2 * NS2], Li[DD], r[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) r[c] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 2 * NS2; ++c) si[c] = 0.0;
 
   // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
   if (active) {
     long long k = min(k0 + e, G.N_e - 1);
     double uu[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) uu[c] = u_q[(k * NC + c) * NQ + i];
+    for (int c = 0; c < NC; ++c) uu[c] = __ldcg(u_q + (k * NC + c) * NQ + i);
 #pragma unroll
-    for (int c = 0; c < DD; ++c) Li[c] = G.L_q[(k * DD + c) * NQ + i];
+    for (int c = 0; c < DD; ++c) Li[c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
     cons_to_state<DIM, LAW>(P, uu, si);
 #pragma unroll
-    for (int c = 0; c < NS; ++c) sS[c * nq + tid] = si[c];
+    for (int c = 0; c < NS2; ++c) sS2[c * nq + tid] = make_double2(si[2 * c], si[2 * c + 1]);
 #pragma unroll
-    for (int c = 0; c < DD; ++c) sL[c * nq + tid] = Li[c];
+    for (int m = 0; m < DIM; ++m) {
+      sLa[m * nq + tid] = make_double2(Li[m], Li[m + DIM]);
+      if constexpr (DIM == 3) sLb[m * nq + tid] = Li[m + 2 * DIM];
+    }
   }
   // ---- phase 1: interface numerical flux at the facet nodes
-  SSE_LOOP(idx, nf) {
-    int j = idx % Nf, ee = idx / Nf;
+  for (int idx = tid; idx < nf; idx += 128) {
+    const int j = idx % NF, ee = idx / NF;
     long long k = min(k0 + ee, G.N_e - 1);
-    long long gj = k * Nf + j;
-    double nJ[DIM], nfv[DIM], sl[NS], fs[NC];
-    const double Jf = G.J_f[gj];
-    const int ext = G.toff[gj];
+    long long gj = k * NF + j;
+    double nJ[DIM], nfv[DIM], sl[2 * NS2], fs[NC];
+    const double Jf = __ldcg(G.J_f + gj);
+    const int ext = __ldcg(G.toff + gj);
 #pragma unroll
-    for (int m = 0; m < DIM; ++m) nJ[m] = G.nJf[gj * DIM + m];
+    for (int m = 0; m < DIM; ++m) nJ[m] = __ldcg(G.nJf + gj * DIM + m);
     const double iJf = frcp(Jf);
 #pragma unroll
     for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
-    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * Nf + j, ext, Nf, nfv, sl, fs);
-    double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * Nf + j] = bj * fs[c];
+    for (int c = 0; c < 2 * NS2; ++c) sl[c] = 0.0;
+    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
+    const double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
-    for (int c = 0; c < NS; ++c) sSf[c * nf + idx] = sl[c];
+    for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * NF + j] = bj * fs[c];
+#pragma unroll
+    for (int c = 0; c < NS2; ++c) sSf2[c * nf + idx] = make_double2(sl[2 * c], sl[2 * c + 1]);
 #pragma unroll
     for (int m = 0; m < DIM; ++m) sNf[m * nf + idx] = 0.5 * nJ[m];
   }
@@ -470,35 +504,42 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phase 2: volume flux differencing, every pair on a tensor line evaluated once
 #pragma unroll
   for (int l = 0; l < DIM; ++l) {
-    const int stride = (l == 0) ? ipow(N1, DIM - 1) : (l == 1 ? ipow(N1, DIM - 2) : 1);
+    constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
+    const int stride = (l == 0) ? s0 : (l == 1 ? s1 : 1);
     const int al = (i / stride) % N1;
     double* buf = sX + (l & 1) * (H * NC * nq);
     if (active) {
-#pragma unroll 1
+#pragma unroll
       for (int o = 1; o <= H; ++o) {
-        const bool mine = (2 * o < N1) || (al < N1 / 2);
+        const bool mine = (N1 % 2 == 1) || (2 * o < N1) || (al < N1 / 2);
         if (mine) {
           int ap = al + o;
           if (ap >= N1) ap -= N1;
           const int jt = tid + (ap - al) * stride;
           const double* Sp = F.Sp + ((l * H + (o - 1)) * DIM) * NQ + i;
-          double sv[DIM], cv[DIM], sj[NS], f[NC];
+          double sv[DIM], cv[DIM], sj[2 * NS2], f[NC];
 #pragma unroll
           for (int m = 0; m < DIM; ++m) {
             const bool used = COLLAPSED ? (m >= l) : (m == l);
             sv[m] = used ? __ldg(Sp + m * NQ) : 0.0;
           }
 #pragma unroll
-          for (int c = 0; c < NS; ++c) sj[c] = sS[c * nq + jt];
+          for (int c = 0; c < NS2; ++c) {
+            const double2 v = sS2[c * nq + jt];
+            sj[2 * c] = v.x;
+            sj[2 * c + 1] = v.y;
+          }
 #pragma unroll
-          for (int n = 0; n < DIM; ++n) {
-            double acc = 0.0;
+          for (int n = 0; n < DIM; ++n) cv[n] = 0.0;
 #pragma unroll
-            for (int m = 0; m < DIM; ++m) {
-              const bool used = COLLAPSED ? (m >= l) : (m == l);
-              if (used) acc = fma(sv[m], Li[m + DIM * n] + sL[(m + DIM * n) * nq + jt], acc);
+          for (int m = 0; m < DIM; ++m) {
+            const bool used = COLLAPSED ? (m >= l) : (m == l);
+            if (used) {
+              const double2 la = sLa[m * nq + jt];
+              cv[0] = fma(sv[m], Li[m] + la.x, cv[0]);
+              cv[1] = fma(sv[m], Li[m + DIM] + la.y, cv[1]);
+              if constexpr (DIM == 3) cv[2] = fma(sv[m], Li[m + 2 * DIM] + sLb[m * nq + jt], cv[2]);
             }
-            cv[n] = acc;
           }
           two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, cv, f);
 #pragma unroll
@@ -513,7 +554,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     if (active) {
 #pragma unroll
       for (int o = 1; o <= H; ++o) {
-        const bool theirs = (2 * o < N1) || (al >= N1 / 2);
+        const bool theirs = (N1 % 2 == 1) || (2 * o < N1) || (al >= N1 / 2);
         if (theirs) {
           int as = al - o;
           if (as < 0) as += N1;
@@ -531,15 +572,24 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     for (int half = 0; half < 2; ++half) {
       __syncthreads();   // previous users of sX (pair buffers / first half) are done
       if (active) {
+        const int kend = (half == 0 ? KH : KC);
+        // software-pipelined table reads: slot kk+1 is fetched while slot kk is evaluated
+        int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node | face << 16
+        double cij = __ldg(F.Cv + (half * KH) * NQ + i);
 #pragma unroll 1
-        for (int kk = half * KH; kk < (half == 0 ? KH : KC); ++kk) {
-          const int jp = __ldg(F.Cj + kk * NQ + i);      // facet node | face << 16
-          const double cij = __ldg(F.Cv + kk * NQ + i);
+        for (int kk = half * KH; kk < kend; ++kk) {
+          const int kn = (kk + 1 < kend) ? kk + 1 : kk;
+          const int jp_next = __ldg(F.Cj + kn * NQ + i);
+          const double cij_next = __ldg(F.Cv + kn * NQ + i);
           const int j = jp & 0xffff, fc = jp >> 16;
-          const int jj = e * Nf + j;
-          double nJ[DIM], sj[NS], f[NC];
+          const int jj = e * NF + j;
+          double nJ[DIM], sj[2 * NS2], f[NC];
 #pragma unroll
-          for (int c = 0; c < NS; ++c) sj[c] = sSf[c * nf + jj];
+          for (int c = 0; c < NS2; ++c) {
+            const double2 v = sSf2[c * nf + jj];
+            sj[2 * c] = v.x;
+            sj[2 * c + 1] = v.y;
+          }
 #pragma unroll
           for (int n = 0; n < DIM; ++n) {
             double acc = 0.0;
@@ -549,20 +599,23 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
             nJ[n] = fma(0.5, acc, sNf[n * nf + jj]);
           }
           two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
+          double* dst = sX + (kk - half * KH) * NC * nq + tid;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            double dlt = cij * f[c];
+            const double dlt = cij * f[c];
             r[c] -= dlt;
-            sX[((kk - half * KH) * NC + c) * nq + tid] = dlt;
+            dst[c * nq] = dlt;
           }
+          jp = jp_next;
+          cij = cij_next;
         }
       }
       __syncthreads();
       // f_f -= column sums of this half's terms (R rows sorted by slot, split at Rmid);
       // Rred holds the ready-made shared-memory offset kk_local*NC*nq + i of each term
-      SSE_LOOP(idx, NC * nf) {
+      for (int idx = tid; idx < NC * nf; idx += 128) {
         const int c = idx % NC, ej = idx / NC;
-        const int j = ej % Nf, ee = ej / Nf;
+        const int j = ej % NF, ee = ej / NF;
         const int b = half == 0 ? __ldg(T.R_rp + j) : __ldg(F.Rmid + j);
         const int en = half == 0 ? __ldg(F.Rmid + j) : __ldg(T.R_rp + j + 1);
         if (en > b) {
@@ -570,7 +623,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
           double acc = 0.0;
 #pragma unroll 5
           for (int q = b; q < en; ++q) acc += base[__ldg(F.Rred + q)];
-          sFf[(ee * NC + c) * Nf + j] -= acc;
+          sFf[(ee * NC + c) * NF + j] -= acc;
         }
       }
     }
@@ -578,21 +631,22 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   __syncthreads();
   // ---- phase 5: r_q -= R^T f_f (ELL), then hand r_q to the modal projection
   if (active) {
-#pragma unroll 1
+#pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
       const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
       const double rv = __ldg(F.Rv + kk * NQ + i);
+      const double* ff = sFf + e * NC * NF + j;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, sFf[(e * NC + c) * Nf + j], r[c]);
+      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
   }
   __syncthreads();
   // ---- phase 6: dudt = M^-1 V^T r_q
-  apply_Vt_t<DIM, N1, NC>(T, E, sR, sM, sX);
-  mass_solve_t<DIM, N1, NC>(T, G, k0, E, sM, sR, sX);
-  store_result(T, G, rk, k0, E, NC, sM, dudt);
+  apply_Vt_t<DIM, N1, NC>(T, EL, sR, sM, sX);
+  mass_solve_t<DIM, N1, NC>(T, G, k0, EL, sM, sR, sX);
+  store_result(T, G, rk, k0, EL, NC, sM, dudt);
 }
 
 }  // namespace sse

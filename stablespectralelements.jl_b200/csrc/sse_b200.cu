@@ -209,11 +209,14 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
 
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
 static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
+  using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
+  if (Cf::NF != h->cfg.N_f) return fail("facet-node count does not match the specialised kernel");
+  const size_t smem = Cf::bytes(h->cfg.N_p);
   CU(cudaFuncSetAttribute(k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_b));
-  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_b - 1) / h->E_b);
-  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, h->thr_b, h->smem_b, h->stream>>>(
-      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->E_b);
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
+  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, 128, smem, h->stream>>>(
+      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -682,6 +685,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
   if (h->fast_b) {
+    h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
     const int KH = (h->kc + 1) / 2;
     std::vector<int> off(h->rred_pk.size());
     for (size_t q = 0; q < off.size(); ++q) {

@@ -128,8 +128,15 @@ class DistributedResidual:
             self.torch = torch
             self.part = partition(sd.mesh.mapP, rank, world)
             self.elements = self.part.elements
-            self.dev = DeviceResidual(solver, device=device, mapP=self.part.mapP_local,
-                                      n_halo=self.part.n_halo, elements=self.elements)
+            if sd.mesh.elem_start is not None:
+                # the discretization already holds only this rank's shard (setup memory ~1/world)
+                if sd.mesh.elem_start != self.part.start or sd.N_e != len(self.elements):
+                    raise ValueError("mesh shard does not match this rank's element range")
+                self.dev = DeviceResidual(solver, device=device, mapP=self.part.mapP_local,
+                                          n_halo=self.part.n_halo)
+            else:
+                self.dev = DeviceResidual(solver, device=device, mapP=self.part.mapP_local,
+                                          n_halo=self.part.n_halo, elements=self.elements)
             self.dev.halo_setup(self.part.send_idx)
             s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
             N_c = self.dev.N_c

@@ -53,6 +53,9 @@ class MeshData:
     mapP: np.ndarray                   # (N_f, N_e) int64, 0-based linear index j + N_f*k
     limits: Tuple[Tuple[float, float], ...]
     FToF: Optional[np.ndarray] = None  # (num_faces, N_e) linear face index f + num_faces*k
+    # element shard (multi-GPU setup): this object holds elements [elem_start, elem_start+N_e)
+    # of a larger mesh whose full connectivity is kept in ``mapP`` (N_f, N_e_global)
+    elem_start: Optional[int] = None
 
     @property
     def N_e(self):
@@ -231,7 +234,9 @@ def _make_mesh(re: RefElemData, VXYZ, EToV, limits, xyz=None, FToF=None, mapP=No
         xyz = tuple(re.V1 @ v[EToV].T for v in VXYZ)
     xyzq = tuple(re.Vq @ x for x in xyz)
     xyzf = tuple(re.Vf @ x for x in xyz)
-    if FToF is None:
+    if FToF is False:
+        FToF = None
+    elif FToF is None:
         FToF = build_face_connectivity(elem, VXYZ, EToV, limits, re.fv)
     if mapP is None:
         mapP = build_mapP(straight_xyzf if straight_xyzf is not None else xyzf, FToF,
@@ -302,6 +307,15 @@ def _warp_coordinates(x, w):
     raise TypeError(w)
 
 
+def mesh_subset(mesh: MeshData, start: int, stop: int) -> MeshData:
+    """Shard [start, stop) of the elements: node coordinates are sliced, the connectivity
+    ``mapP`` stays global (the partitioner needs it), ``elem_start`` records the offset."""
+    sl = slice(start, stop)
+    cut = lambda t: tuple(np.ascontiguousarray(x[:, sl]) for x in t)
+    return MeshData(mesh.VXYZ, mesh.EToV[sl], cut(mesh.xyz), cut(mesh.xyzq), cut(mesh.xyzf),
+                    mesh.mapP, mesh.limits, None, elem_start=start)
+
+
 def warp_mesh(mesh: MeshData, reference, warping=0.2, L: float = 1.0) -> MeshData:
     """mesh.jl:23-120: apply the warp to the mapping nodes and rebuild node coordinates.
 
@@ -314,5 +328,7 @@ def warp_mesh(mesh: MeshData, reference, warping=0.2, L: float = 1.0) -> MeshDat
     if isinstance(warping, (int, float)):
         warping = DelReyWarping(float(warping), tuple(float(L) for _ in range(d)))
     xyz_new = _warp_coordinates(mesh.xyz, warping)
-    return _make_mesh(re, mesh.VXYZ, mesh.EToV, mesh.limits, xyz=tuple(xyz_new),
-                      FToF=mesh.FToF, mapP=mesh.mapP)
+    out = _make_mesh(re, mesh.VXYZ, mesh.EToV, mesh.limits, xyz=tuple(xyz_new),
+                     FToF=mesh.FToF if mesh.FToF is not None else False, mapP=mesh.mapP)
+    out.elem_start = mesh.elem_start
+    return out

@@ -69,7 +69,7 @@ def advection_tet_case(p=4, M=2, lazy=True, warp=0.1, mapping_degree=None):
 
 
 def euler_tet_case(p=4, M=2, lazy=True, warp=False, interface="lf", ic="tgv",
-                   approx="modal"):
+                   approx="modal", shard=None):
     """BASELINE config 4 (north star): 3-D Euler Taylor-Green vortex on tetrahedra, flux
     differencing, entropy-conservative two-point flux, LF or EC interface flux."""
     g = 1.4
@@ -78,6 +78,10 @@ def euler_tet_case(p=4, M=2, lazy=True, warp=False, interface="lf", ic="tgv",
     at = ModalTensor(p) if approx == "modal" else NodalTensor(p)
     ra = make_reference_approximation(at, Tet(), mapping_degree=(min(p, 3) if warp else 1))
     mesh = uniform_periodic_mesh(ra, ((0.0, L),) * 3, (M,) * 3)
+    if shard is not None:      # (rank, world): keep only this rank's elements from here on
+        from sse_b200.distributed import element_ranges
+        from sse_b200.mesh import mesh_subset
+        mesh = mesh_subset(mesh, *element_ranges(mesh.N_e, shard[1])[shard[0]])
     if warp:
         mesh = warp_mesh(mesh, ra, ChanWarping(1 / 16, (L, L, L)))
         sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
