@@ -26,6 +26,11 @@ struct FastTables {
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
 
+// A[a1][b1] = sqrt(2) P_b1(eta1_a1) of the warped product (tensor_simplex.jl:84-140), one slot
+// per N1 in {3,4,5}.  With fully unrolled loops the entries become constant-bank operands of
+// the DFMAs (no load instructions) in the first-direction contractions below.
+__constant__ double c_wA[3][25];
+
 // ---------------------------------------------------------------- sum-factorised V, V^T
 // src [E][NC][N_p] -> dst [E][NC][NQ]; every thread carries all NC components of one output.
 template <int DIM, int N1, int NC>
@@ -130,19 +135,20 @@ __device__ __forceinline__ void apply_V_t(const Tables& T, int E, const double* 
       for (int c = 0; c < NC; ++c) Wt[(e * NC + c) * N3 + (b1 * N1 + a2) * N1 + a3] = acc[c];
     }
     __syncthreads();
-    SSE_LOOP(idx, E * N3) {
-      int a23 = idx % N2, a1 = (idx / N2) % N1, e = idx / N3;
-      double acc[NC];
+    // first direction: one thread per (component, a2, a3) produces all N1 outputs along a1,
+    // so every W value is loaded once and A comes from the constant bank
+    SSE_LOOP(idx, E * NC * N2) {
+      int a23 = idx % N2, ec = idx / N2;
+      double w[N1];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+      for (int b1 = 0; b1 < N1; ++b1) w[b1] = Wt[ec * N3 + b1 * N2 + a23];
 #pragma unroll
-      for (int b1 = 0; b1 < N1; ++b1) {
-        double v = __ldg(T.wA + a1 * N1 + b1);
+      for (int a1 = 0; a1 < N1; ++a1) {
+        double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = fma(v, Wt[(e * NC + c) * N3 + b1 * N2 + a23], acc[c]);
+        for (int b1 = 0; b1 < N1; ++b1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], w[b1], acc);
+        dst[ec * NQ + a1 * N2 + a23] = acc;
       }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) dst[(e * NC + c) * NQ + a1 * N2 + a23] = acc[c];
     }
     __syncthreads();
   }
@@ -216,19 +222,18 @@ __device__ __forceinline__ void apply_Vt_t(const Tables& T, int E, const double*
     constexpr int N2 = N1 * N1, N3 = N1 * N1 * N1;
     double* Wt = tmp;               // [E][NC][b1][a2][a3]
     double* Z = tmp + E * NC * N3;  // [E][NC][b1][b2][a3]
-    SSE_LOOP(idx, E * N3) {
-      int a23 = idx % N2, b1 = (idx / N2) % N1, e = idx / N3;
-      double acc[NC];
+    SSE_LOOP(idx, E * NC * N2) {
+      int a23 = idx % N2, ec = idx / N2;
+      double x[N1];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+      for (int a1 = 0; a1 < N1; ++a1) x[a1] = src[ec * NQ + a1 * N2 + a23];
 #pragma unroll
-      for (int a1 = 0; a1 < N1; ++a1) {
-        double v = __ldg(T.wA + a1 * N1 + b1);
+      for (int b1 = 0; b1 < N1; ++b1) {
+        double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + a1 * N2 + a23], acc[c]);
+        for (int a1 = 0; a1 < N1; ++a1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], x[a1], acc);
+        Wt[ec * N3 + b1 * N2 + a23] = acc;
       }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) Wt[(e * NC + c) * N3 + b1 * N2 + a23] = acc[c];
     }
     __syncthreads();
     SSE_LOOP(idx, E * N3) {

@@ -58,20 +58,25 @@ __device__ __forceinline__ void logmean_terms(double x, double y, double& num, d
   num = 105.0 * s * t * t * t;
 }
 
+// rare branch (|x-y|/(x+y) >= 1e-2): kept out of line so the common path stays small
+__device__ __noinline__ double logmean_full(double x, double y) { return (y - x) / log(y / x); }
+
 __device__ __forceinline__ double logmean(double x, double y) {
   double num, den;
   bool taylor;
   logmean_terms(x, y, num, den, taylor);
-  if (taylor) return fdiv(num, den);
-  return (y - x) / log(y / x);
+  double r = fdiv(num, den);
+  if (!taylor) r = logmean_full(x, y);
+  return r;
 }
 
 __device__ __forceinline__ double inv_logmean(double x, double y) {
   double num, den;
   bool taylor;
   logmean_terms(x, y, num, den, taylor);
-  if (taylor) return fdiv(den, num);
-  return log(y / x) / (y - x);
+  double r = fdiv(den, num);
+  if (!taylor) r = frcp(logmean_full(x, y));
+  return r;
 }
 
 // conservative -> shared-memory state

@@ -68,6 +68,7 @@ struct sse_handle {
   FastTables F{};
   int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
   std::vector<int> rred_pk;
+  int const_conflict = 0;
 };
 
 template <typename Tp>
@@ -360,6 +361,21 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     if (d == 3 && dev_upload(h, ops->warp_C, (size_t)n * n * n * n, &pC)) return -1;
     if (dev_upload(h, ops->sigma_i, nd, &ps)) return -1;
     T.wA = pA; T.wB = pB; T.wC = pC; T.sig = ps;
+    if (n >= 3 && n <= 5) {
+      // constant-bank copy of A for the specialised kernels (one slot per n); two handles with
+      // different A tables for the same n cannot share it
+      static double seen[3][25];
+      static bool have[3] = {false, false, false};
+      bool same = true;
+      for (int q = 0; q < n * n; ++q) same = same && (!have[n - 3] || seen[n - 3][q] == ops->warp_A[q]);
+      if (!same) h->const_conflict = 1;
+      else {
+        for (int q = 0; q < n * n; ++q) seen[n - 3][q] = ops->warp_A[q];
+        have[n - 3] = true;
+        CU(cudaMemcpyToSymbol(c_wA, ops->warp_A, sizeof(double) * n * n,
+                              sizeof(double) * 25 * (n - 3)));
+      }
+    }
   } else if (cfg->v_kind == SSE_V_IDENTITY) {
     if (Np != Nq) return fail("identity V needs N_p = N_q");
   } else {
@@ -658,7 +674,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     for (int m = 0; m < d; ++m) nd1 *= (size_t)std::max(n1, 1);
     const bool mass_ok = !ops->Minv && (cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED ||
                                          cfg->mass_solver == SSE_MASS_DIAGONAL);
-    const bool force_generic = getenv("SSE_B200_GENERIC") != nullptr;
+    const bool force_generic = getenv("SSE_B200_GENERIC") != nullptr || h->const_conflict;
     if (!force_generic && !h->second_order && cfg->strategy == SSE_REFERENCE_OPERATOR &&
         (int)nd1 == Nq && mass_ok)
       h->fast_a = fast_a_key(d, n1, law_t);
