@@ -25,6 +25,10 @@ struct Tables {
   const double *wA, *wB, *wC;          // warped-product tables
   const int *sig;                      // sigma_i (n1^d), -1 where unused
   const int *R_rp, *R_ci;  const double *R_v;  const int *R_slot;   // R rows -> Rt entry ids
+  // arithmetic-progression descriptor of R row j (tensor-product elements; else NULL):
+  // columns start + q*stride, q < count; ELL slot k of this facet node in the rows of R^T.
+  // packed start | stride << 10 | count << 20 | k << 27
+  const int *R_desc;
   const int *Rt_rp, *Rt_ci; const double *Rt_v; const double *C_v;  // R^T rows; C = R^T B
   const int *S_rp, *S_ci;  const double *S_v;                       // S_v[e*dim + m]
   const int *D_rp[3], *D_ci[3];  const double *D_v[3];

@@ -20,8 +20,6 @@ struct FastTables {
   const int* Cj;       // [KC][NQ] facet node of ELL slot k | (face index << 16)
   const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
   const double* Rv;    // [KC][NQ] R[j, i]
-  const int* Rred;     // per R-CSR entry (rows sorted by slot): (k mod KH)*NC*(E*NQ) + i
-  const int* Rmid;     // [N_f] first entry of row j whose slot k >= ceil(KC/2)
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -31,10 +29,21 @@ __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * i
 // the DFMAs (no load instructions) in the first-direction contractions below.
 __constant__ double c_wA[3][25];
 
+// the few table pointers the V / V^T applies need, passed BY VALUE to the out-of-line functions
+// (a reference to the kernel-parameter struct would force a local-memory copy of all of it)
+struct VTab {
+  const double *wA, *wB, *wC, *Vd, *VdT;
+  const int* sig;
+  int N_p, v_kind;
+};
+__device__ __forceinline__ VTab vtab(const Tables& T) {
+  return VTab{T.wA, T.wB, T.wC, T.Vd, T.VdT, T.sig, T.N_p, T.v_kind};
+}
+
 // ---------------------------------------------------------------- sum-factorised V, V^T
 // src [E][NC][N_p] -> dst [E][NC][NQ]; every thread carries all NC components of one output.
-template <int DIM, int N1, int NC>
-__device__ __forceinline__ void apply_V_t(const Tables& T, int E, const double* __restrict__ src,
+template <int DIM, int N1, int NC, int E>
+__device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ src,
                                           double* __restrict__ dst, double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
   const int Np = T.N_p;
@@ -155,8 +164,8 @@ __device__ __forceinline__ void apply_V_t(const Tables& T, int E, const double* 
 }
 
 // src [E][NC][NQ] -> dst [E][NC][N_p]
-template <int DIM, int N1, int NC>
-__device__ __forceinline__ void apply_Vt_t(const Tables& T, int E, const double* __restrict__ src,
+template <int DIM, int N1, int NC, int E>
+__device__ __noinline__ void apply_Vt_t(const VTab T, const double* __restrict__ src,
                                            double* __restrict__ dst, double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
   const int Np = T.N_p;
@@ -276,22 +285,26 @@ __device__ __forceinline__ void apply_Vt_t(const Tables& T, int E, const double*
   }
 }
 
-// dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread
-template <int NQ, int NC>
-__device__ __forceinline__ void apply_R_t(const Tables& T, int E, const double* __restrict__ src,
+// dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread.  Rows of R on tensor-product
+// elements touch an arithmetic progression of volume nodes (one tensor line, or the N1 x N1
+// block behind a node of the collapsed face), so no column indices are loaded.
+template <int NQ, int NC, int E, int Nf>
+__device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restrict__ src,
                                           double* __restrict__ dst) {
-  const int Nf = T.N_f;
   SSE_LOOP(idx, E * Nf) {
     int j = idx % Nf, e = idx / Nf;
     double acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-    const int b = __ldg(T.R_rp + j), en = __ldg(T.R_rp + j + 1);
-    for (int q = b; q < en; ++q) {
-      double v = __ldg(T.R_v + q);
-      int i = __ldg(T.R_ci + q);
+    const int b = __ldg(T.R_rp + j);
+    const int desc = __ldg(T.R_desc + j);
+    const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
+    const double* s0 = src + e * NC * NQ + start;
+#pragma unroll 5
+    for (int q = 0; q < cnt; ++q) {
+      double v = __ldg(T.R_v + b + q);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * NQ + i], acc[c]);
+      for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Nf + j] = acc[c];
@@ -300,8 +313,8 @@ __device__ __forceinline__ void apply_R_t(const Tables& T, int E, const double* 
 }
 
 // weight-adjusted (M^-1 = I) or diagonal mass solve, in place on rhs [E][NC][N_p]
-template <int DIM, int N1, int NC>
-__device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long long k0, int E,
+template <int DIM, int N1, int NC, int E>
+__device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long long k0,
                                              double* __restrict__ rhs, double* __restrict__ q,
                                              double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
@@ -314,7 +327,7 @@ __device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long
     __syncthreads();
     return;
   }
-  apply_V_t<DIM, N1, NC>(T, E, rhs, q, tmp);
+  apply_V_t<DIM, N1, NC, E>(vtab(T), rhs, q, tmp);
   SSE_LOOP(idx, E * NQ) {
     int i = idx % NQ, e = idx / NQ;
     long long k = min(k0 + e, G.N_e - 1);
@@ -323,19 +336,28 @@ __device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long
     for (int c = 0; c < NC; ++c) q[(e * NC + c) * NQ + i] *= sc;
   }
   __syncthreads();
-  apply_Vt_t<DIM, N1, NC>(T, E, q, rhs, tmp);
+  apply_Vt_t<DIM, N1, NC, E>(vtab(T), q, rhs, tmp);
 }
 
 // =========================================================================== loop A
+// facet nodes of a tensor-product element
+template <int DIM, int N1, bool COLLAPSED>
+struct TensorNF {
+  static constexpr int value = COLLAPSED ? (DIM == 3 ? 4 * N1 * N1 : 3 * N1)
+                                         : 2 * DIM * ipow(N1, DIM - 1);
+};
+
 // shared: bufP[E*NC*N_p] | bufQ[E*NC*NQ] | bufQ2[E*NC*NQ] | bufF[E*NC*N_f] | tmp[2*E*NC*NQ]
-template <int DIM, int N1, int LAW>
-__global__ void __launch_bounds__(256)
+template <int DIM, int N1, int LAW, bool COLLAPSED>
+__global__ void __launch_bounds__(128)
 k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
-               double* __restrict__ u_f, int E, int proj) {
+               double* __restrict__ u_f, int proj) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NQ = ipow(N1, DIM);
-  extern __shared__ double sm[];
-  const int Np = T.N_p, Nf = T.N_f;
+  constexpr int E = (128 / NQ) > 0 ? 128 / NQ : 1;
+  constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
+  extern __shared__ __align__(16) double sm[];
+  const int Np = T.N_p;
   double* bufP = sm;
   double* bufQ = bufP + E * NC * Np;
   double* bufQ2 = bufQ + E * NC * NQ;
@@ -344,11 +366,11 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
-  SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? u[k0 * NC * Np + idx] : 1.0;
+  SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? __ldcg(u + k0 * NC * Np + idx) : 1.0;
   __syncthreads();
-  apply_V_t<DIM, N1, NC>(T, E, bufP, bufQ, tmp);
+  apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
-    apply_R_t<NQ, NC>(T, E, bufQ, bufF);
+    apply_R_t<NQ, NC, E, Nf>(T, bufQ, bufF);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
     SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
     return;
@@ -362,39 +384,37 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     double sc = 1.0;
     if (proj == 2) {
       long long k = min(k0 + e, G.N_e - 1);
-      sc = __ldg(T.W + i) * G.J_q[k * NQ + i];
+      sc = __ldg(T.W + i) * __ldcg(G.J_q + k * NQ + i);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) bufQ2[(e * NC + c) * NQ + i] = w[c] * sc;
   }
   __syncthreads();
   if (proj == 2) {
-    apply_Vt_t<DIM, N1, NC>(T, E, bufQ2, bufP, tmp);
-    mass_solve_t<DIM, N1, NC>(T, G, k0, E, bufP, bufQ2, tmp);
-    apply_V_t<DIM, N1, NC>(T, E, bufP, bufQ2, tmp);
+    apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ2, bufP, tmp);
+    mass_solve_t<DIM, N1, NC, E>(T, G, k0, bufP, bufQ2, tmp);
+    apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ2, tmp);
   }
-  apply_R_t<NQ, NC>(T, E, bufQ2, bufF);
-  if (proj == 2) {
-    SSE_LOOP(idx, Ev * NQ) {
-      int i = idx % NQ, e = idx / NQ;
-      double w[NC], uu[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) w[c] = bufQ2[(e * NC + c) * NQ + i];
-      entropy_to_cons<DIM, LAW>(P, w, uu);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) u_q[((k0 + e) * NC + c) * NQ + i] = uu[c];
-    }
-  } else {
+  apply_R_t<NQ, NC, E, Nf>(T, bufQ2, bufF);
+  if (proj != 2) {
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
   }
-  SSE_LOOP(idx, Ev * Nf) {
-    int j = idx % Nf, e = idx / Nf;
+  // entropy -> conservative variables at the volume nodes (modal case) and the facet nodes,
+  // one loop so the log/exp sequence is instantiated once
+  const int nvol = (proj == 2) ? Ev * NQ : 0;
+  SSE_LOOP(idx, nvol + Ev * Nf) {
+    const bool vol = idx < nvol;
+    const int ii = vol ? idx : idx - nvol;
+    const int npt = vol ? NQ : Nf;
+    const int pt = ii % npt, e = ii / npt;
+    const double* srcw = vol ? bufQ2 : bufF;
     double w[NC], uu[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) w[c] = bufF[(e * NC + c) * Nf + j];
+    for (int c = 0; c < NC; ++c) w[c] = srcw[(e * NC + c) * npt + pt];
     entropy_to_cons<DIM, LAW>(P, w, uu);
+    double* dstu = vol ? u_q : u_f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) u_f[((k0 + e) * NC + c) * Nf + j] = uu[c];
+    for (int c = 0; c < NC; ++c) dstu[((k0 + e) * NC + c) * npt + pt] = uu[c];
   }
 }
 
@@ -616,18 +636,19 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
         }
       }
       __syncthreads();
-      // f_f -= column sums of this half's terms (R rows sorted by slot, split at Rmid);
-      // Rred holds the ready-made shared-memory offset kk_local*NC*nq + i of each term
+      // f_f -= column sums of this half's terms: the terms of facet node j sit in ELL slot k
+      // at an arithmetic progression of volume nodes (R_desc), no index loads
       for (int idx = tid; idx < NC * nf; idx += 128) {
         const int c = idx % NC, ej = idx / NC;
         const int j = ej % NF, ee = ej / NF;
-        const int b = half == 0 ? __ldg(T.R_rp + j) : __ldg(F.Rmid + j);
-        const int en = half == 0 ? __ldg(F.Rmid + j) : __ldg(T.R_rp + j + 1);
-        if (en > b) {
-          const double* base = sX + c * nq + ee * NQ;
+        const int desc = __ldg(T.R_desc + j);
+        const int kslot = (desc >> 27) & 31;
+        if ((half == 0) == (kslot < KH)) {
+          const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
+          const double* base = sX + ((kslot - half * KH) * NC + c) * nq + ee * NQ + start;
           double acc = 0.0;
 #pragma unroll 5
-          for (int q = b; q < en; ++q) acc += base[__ldg(F.Rred + q)];
+          for (int q = 0; q < cnt; ++q) acc += base[q * stride];
           sFf[(ee * NC + c) * NF + j] -= acc;
         }
       }
@@ -649,8 +670,8 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   }
   __syncthreads();
   // ---- phase 6: dudt = M^-1 V^T r_q
-  apply_Vt_t<DIM, N1, NC>(T, EL, sR, sM, sX);
-  mass_solve_t<DIM, N1, NC>(T, G, k0, EL, sM, sR, sX);
+  apply_Vt_t<DIM, N1, NC, EL>(vtab(T), sR, sM, sX);
+  mass_solve_t<DIM, N1, NC, EL>(T, G, k0, sM, sR, sX);
   store_result(T, G, rk, k0, EL, NC, sM, dudt);
 }
 

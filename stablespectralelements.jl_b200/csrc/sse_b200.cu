@@ -67,8 +67,8 @@ struct sse_handle {
   // compile-time specialised tensor-product path
   FastTables F{};
   int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
-  std::vector<int> rred_pk;
   int const_conflict = 0;
+  bool r_ap = false;
 };
 
 template <typename Tp>
@@ -198,11 +198,18 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
 
 template <int DIM, int N1, int LAW>
 static int launch_a_fast(sse_handle* h, const double* u_dev) {
-  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_a));
-  int grid = (int)((h->G.N_e - h->G.k_begin + h->E_a - 1) / h->E_a);
-  k_nodal_tensor<DIM, N1, LAW><<<grid, h->thr_a, h->smem_a, h->stream>>>(
-      h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->E_a, h->proj);
+  constexpr int NQ = ipow(N1, DIM);
+  constexpr int EL = (128 / NQ) > 0 ? 128 / NQ : 1;
+  if (TensorNF<DIM, N1, true>::value != h->cfg.N_f)
+    return fail("facet-node count does not match the specialised kernel");
+  const int Nc = h->cfg.N_c;
+  const size_t smem = sizeof(double) * (size_t)EL *
+                      ((size_t)Nc * h->cfg.N_p + 4 * (size_t)Nc * NQ + (size_t)Nc * h->cfg.N_f);
+  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
+  k_nodal_tensor<DIM, N1, LAW, true><<<grid, 128, smem, h->stream>>>(
+      h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -400,6 +407,25 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       Rslot[e] = slot;
     }
   T.nnzRt = (int)Rt.ci.size();
+  {
+    // arithmetic-progression descriptors of the rows of R (tensor-product elements)
+    std::vector<int> desc(Nf, 0);
+    bool ap = Nq < 1024;
+    for (int j = 0; j < Nf && ap; ++j) {
+      int b = R.rp[j], en = R.rp[j + 1], cnt = en - b;
+      if (cnt < 1 || cnt > 127) { ap = false; break; }
+      int start = R.ci[b], stride = cnt > 1 ? R.ci[b + 1] - R.ci[b] : 0;
+      int k = Rslot[b] - Rt.rp[R.ci[b]];
+      for (int q = 0; q < cnt; ++q) {
+        if (R.ci[b + q] != start + q * stride) ap = false;
+        if (Rslot[b + q] - Rt.rp[R.ci[b + q]] != k) ap = false;
+      }
+      if (stride < 0 || stride > 1023 || k > 31) ap = false;
+      desc[j] = start | (stride << 10) | (cnt << 20) | (k << 27);
+    }
+    h->r_ap = ap;
+    if (ap && dev_upload_vec(h, desc, &T.R_desc)) return -1;
+  }
   if (dev_upload_vec(h, R.rp, &T.R_rp) || dev_upload_vec(h, R.ci, &T.R_ci) ||
       dev_upload_vec(h, R.v, &T.R_v) || dev_upload_vec(h, Rslot, &T.R_slot) ||
       dev_upload_vec(h, Rt.rp, &T.Rt_rp) || dev_upload_vec(h, Rt.ci, &T.Rt_ci) ||
@@ -507,7 +533,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
                 for (int m = 0; m < d; ++m)
                   Sp[(((size_t)l * H + (o - 1)) * d + m) * Nq + i] = S[m][(size_t)i * Nq + j];
               }
-          std::vector<int> Cj((size_t)kc * Nq), Rred(R.ci.size());
+          std::vector<int> Cj((size_t)kc * Nq);
           std::vector<double> Cvv((size_t)kc * Nq), Rvv((size_t)kc * Nq);
           for (int i = 0; i < Nq; ++i)
             for (int q = 0; q < kc; ++q) {
@@ -516,28 +542,10 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
               Cvv[(size_t)q * Nq + i] = Cv[en];
               Rvv[(size_t)q * Nq + i] = Rt.v[en];
             }
-          std::vector<int> Rmid(Nf);
-          const int KH = (kc + 1) / 2;
-          for (int j = 0; j < Nf; ++j) {
-            std::vector<int> row;
-            for (int en = R.rp[j]; en < R.rp[j + 1]; ++en) {
-              int i = R.ci[en];
-              row.push_back((Rslot[en] - Rt.rp[i]) * Nq + i);
-            }
-            std::sort(row.begin(), row.end());          // by slot k, then node
-            int mid = R.rp[j + 1];
-            for (size_t q = 0; q < row.size(); ++q) {
-              Rred[R.rp[j] + q] = row[q];
-              if (row[q] / Nq >= KH && mid == R.rp[j + 1]) mid = R.rp[j] + (int)q;
-            }
-            Rmid[j] = mid;
-          }
-          if (Nf >= 65536) ok = false;
+          if (Nf >= 65536 || !h->r_ap) ok = false;
           if (ok && (dev_upload_vec(h, Sp, &h->F.Sp) || dev_upload_vec(h, Cj, &h->F.Cj) ||
-                     dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv) ||
-                     dev_upload_vec(h, Rmid, &h->F.Rmid)))
+                     dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv)))
             return -1;
-          h->rred_pk = Rred;   // turned into shared-memory offsets once E is known
           h->fast_b = ok ? 1 : 0;
           h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
         }
@@ -676,7 +684,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
                                          cfg->mass_solver == SSE_MASS_DIAGONAL);
     const bool force_generic = getenv("SSE_B200_GENERIC") != nullptr || h->const_conflict;
     if (!force_generic && !h->second_order && cfg->strategy == SSE_REFERENCE_OPERATOR &&
-        (int)nd1 == Nq && mass_ok)
+        (int)nd1 == Nq && mass_ok && h->r_ap && ops->Lambda_ref != nullptr &&
+        Nf == (d == 3 ? 4 * n1 * n1 : 3 * n1))
       h->fast_a = fast_a_key(d, n1, law_t);
     if (h->fast_b && !force_generic)
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
@@ -700,17 +709,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
-  if (h->fast_b) {
-    h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
-    const int KH = (h->kc + 1) / 2;
-    std::vector<int> off(h->rred_pk.size());
-    for (size_t q = 0; q < off.size(); ++q) {
-      int k = h->rred_pk[q] / Nq, i = h->rred_pk[q] % Nq;
-      int kl = k >= KH ? k - KH : k;
-      off[q] = kl * Nc * (h->E_b * Nq) + i;
-    }
-    if (dev_upload_vec(h, off, &h->F.Rred)) return -1;
-  }
+  if (h->fast_b) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
