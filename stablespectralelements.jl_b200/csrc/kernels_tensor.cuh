@@ -20,6 +20,7 @@ struct FastTables {
   const int* Cj;       // [KC][NQ] facet node of ELL slot k | (face index << 16)
   const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
   const double* Rv;    // [KC][NQ] R[j, i]
+  const double* D1;    // [DIM][N1][N1] 1-D derivative matrices of D_eta (row-major)
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -288,7 +289,7 @@ __device__ __noinline__ void apply_Vt_t(const VTab T, const double* __restrict__
 // dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread.  Rows of R on tensor-product
 // elements touch an arithmetic progression of volume nodes (one tensor line, or the N1 x N1
 // block behind a node of the collapsed face), so no column indices are loaded.
-template <int NQ, int NC, int E, int Nf>
+template <int NQ, int NC, int E, int Nf, int N1>
 __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restrict__ src,
                                           double* __restrict__ dst) {
   SSE_LOOP(idx, E * Nf) {
@@ -300,11 +301,26 @@ __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restr
     const int desc = __ldg(T.R_desc + j);
     const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
     const double* s0 = src + e * NC * NQ + start;
-#pragma unroll 5
-    for (int q = 0; q < cnt; ++q) {
-      double v = __ldg(T.R_v + b + q);
+    if (cnt == N1) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
+      for (int q = 0; q < N1; ++q) {
+        double v = __ldg(T.R_v + b + q);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
+      }
+    } else if (cnt == N1 * N1 && stride == 1) {
+#pragma unroll
+      for (int q = 0; q < N1 * N1; ++q) {
+        double v = __ldg(T.R_v + b + q);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q], acc[c]);
+      }
+    } else {
+      for (int q = 0; q < cnt; ++q) {
+        double v = __ldg(T.R_v + b + q);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
+      }
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Nf + j] = acc[c];
@@ -370,7 +386,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   __syncthreads();
   apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
-    apply_R_t<NQ, NC, E, Nf>(T, bufQ, bufF);
+    apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
     SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
     return;
@@ -395,7 +411,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     mass_solve_t<DIM, N1, NC, E>(T, G, k0, bufP, bufQ2, tmp);
     apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ2, tmp);
   }
-  apply_R_t<NQ, NC, E, Nf>(T, bufQ2, bufF);
+  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ2, bufF);
   if (proj != 2) {
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
   }
@@ -647,8 +663,15 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
           const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
           const double* base = sX + ((kslot - half * KH) * NC + c) * nq + ee * NQ + start;
           double acc = 0.0;
-#pragma unroll 5
-          for (int q = 0; q < cnt; ++q) acc += base[q * stride];
+          if (cnt == N1) {                       // one tensor line
+#pragma unroll
+            for (int q = 0; q < N1; ++q) acc += base[q * stride];
+          } else if (cnt == N1 * N1 && stride == 1) {   // block behind a collapsed-face node
+#pragma unroll
+            for (int q = 0; q < N1 * N1; ++q) acc += base[q];
+          } else {
+            for (int q = 0; q < cnt; ++q) acc += base[q * stride];
+          }
           sFf[(ee * NC + c) * NF + j] -= acc;
         }
       }
@@ -670,6 +693,181 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   }
   __syncthreads();
   // ---- phase 6: dudt = M^-1 V^T r_q
+  apply_Vt_t<DIM, N1, NC, EL>(vtab(T), sR, sM, sX);
+  mass_solve_t<DIM, N1, NC, EL>(T, G, k0, sM, sR, sX);
+  store_result(T, G, rk, k0, EL, NC, sM, dudt);
+}
+
+// ============================================ loop B, standard form, reference operators
+// time_derivative! of standard_form_first_order.jl:16-63 on tensor-product elements
+// (skew-symmetric split form; see k_standard_ref for the algebra).  HBM-bound: per element it
+// streams Λ_q (d*d*N_q), J_q, nJf, J_f, the traces and u_q once and writes dudt; everything else
+// lives in shared memory / registers.  D_eta^m = I ⊗ D1[m] ⊗ I acts along tensor lines, with
+// the three 1-D matrices staged in shared memory.
+// shared (doubles): sF[DIM][NC][nq] | sG[DIM][NC][nq] | sFf[EL][NC][NF] | sD[DIM][N1][N1] |
+//                   sR[EL][NC][NQ] | sM[EL][NC][Np] | sX[2*NC*nq]
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+struct STCfg {
+  static constexpr int NC = LawTraits<DIM, LAW>::NC;
+  static constexpr int NQ = ipow(N1, DIM);
+  static constexpr int EL = (128 / NQ) > 0 ? 128 / NQ : 1;
+  static constexpr int NF = TensorNF<DIM, N1, COLLAPSED>::value;
+  static constexpr int nq = EL * NQ, nf = EL * NF;
+  static constexpr int oF = 0;
+  static constexpr int oG = oF + DIM * NC * nq;
+  static constexpr int oFf = oG + DIM * NC * nq;
+  static constexpr int oD = oFf + NC * nf;
+  static constexpr int oR = oD + DIM * N1 * N1;
+  static __host__ __device__ constexpr int oM() { return oR + NC * nq; }
+  static __host__ __device__ constexpr int oX(int Np) { return oM() + EL * NC * Np; }
+  static __host__ __device__ constexpr size_t bytes(int Np) {
+    return sizeof(double) * (size_t)(oX(Np) + 2 * NC * nq);
+  }
+};
+
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(128)
+k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
+                  const double* __restrict__ u_f, double* __restrict__ dudt) {
+  using Cf = STCfg<DIM, N1, LAW, COLLAPSED, KC>;
+  constexpr int NC = Cf::NC, NQ = Cf::NQ, NF = Cf::NF, EL = Cf::EL, nq = Cf::nq, nf = Cf::nf;
+  constexpr int NS = LawTraits<DIM, LAW>::NS;
+  constexpr int DD = DIM * DIM;
+  extern __shared__ __align__(16) double sm[];
+  const int Np = T.N_p;
+  double* sF = sm + Cf::oF;
+  double* sG = sm + Cf::oG;
+  double* sFf = sm + Cf::oFf;
+  double* sD = sm + Cf::oD;
+  double* sR = sm + Cf::oR;
+  double* sM = sm + Cf::oM();
+  double* sX = sm + Cf::oX(Np);
+  const long long k0 = G.k_begin + (long long)blockIdx.x * EL;
+  const int tid = threadIdx.x;
+  const bool active = tid < nq;
+  const int e = active ? tid / NQ : 0;
+  const int i = active ? tid % NQ : 0;
+
+  // 1-D derivative matrices (row-major [l][a][b] = D1_l[a][b])
+  for (int idx = tid; idx < DIM * N1 * N1; idx += 128) sD[idx] = __ldg(F.D1 + idx);
+
+  double H[DD];   // H[m + DIM*n] = ½ W Λ_η[i, m, n]
+  // ---- phase 0: physical flux, collapsed metrics, g_m = Σ_n H[m][n] f_n
+  if (active) {
+    long long k = min(k0 + e, G.N_e - 1);
+    double uu[NC], s[NS], Lq[DD];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) uu[c] = __ldcg(u_q + (k * NC + c) * NQ + i);
+#pragma unroll
+    for (int c = 0; c < DD; ++c) Lq[c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
+    cons_to_state<DIM, LAW>(P, uu, s);
+    const double hw = 0.5 * __ldg(T.W + i);
+#pragma unroll
+    for (int m = 0; m < DIM; ++m)
+#pragma unroll
+      for (int n = 0; n < DIM; ++n) {
+        double v;
+        if constexpr (COLLAPSED) {
+          v = 0.0;
+#pragma unroll
+          for (int l = 0; l < DIM; ++l)
+            if (l >= m)   // Λ_ref is upper triangular in collapsed coordinates
+              v = fma(__ldg(T.Gref + (i * DIM + m) * DIM + l), Lq[l + DIM * n], v);
+        } else {
+          v = Lq[m + DIM * n];
+        }
+        H[m + DIM * n] = hw * v;
+      }
+    double fq[DIM][NC];
+#pragma unroll
+    for (int n = 0; n < DIM; ++n) {
+      double cdir[DIM];
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) cdir[m] = (m == n) ? 1.0 : 0.0;
+      physical_flux_c<DIM, LAW>(P, s, cdir, fq[n]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sF[(n * NC + c) * nq + tid] = fq[n][c];
+    }
+#pragma unroll
+    for (int m = 0; m < DIM; ++m)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double g = 0.0;
+#pragma unroll
+        for (int n = 0; n < DIM; ++n) g = fma(H[m + DIM * n], fq[n][c], g);
+        sG[(m * NC + c) * nq + tid] = g;
+      }
+  }
+  __syncthreads();
+  // ---- phase 1: facet nodes: f_f = B J_f (f* − Σ_n ½ n_n (R f_n))
+  for (int idx = tid; idx < nf; idx += 128) {
+    const int j = idx % NF, ee = idx / NF;
+    long long k = min(k0 + ee, G.N_e - 1);
+    long long gj = k * NF + j;
+    double nfv[DIM], sl[NS], fs[NC];
+    const double Jf = __ldcg(G.J_f + gj);
+    const int ext = __ldcg(G.toff + gj);
+    const double iJf = frcp(Jf);
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) nfv[m] = __ldcg(G.nJf + gj * DIM + m) * iJf;
+    interface_flux<DIM, LAW>(P, 0, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
+    const int b = __ldg(T.R_rp + j);
+    const int desc = __ldg(T.R_desc + j);
+    const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
+    for (int q = 0; q < cnt; ++q) {
+      const double rv = __ldg(T.R_v + b + q);
+      const int ii = ee * NQ + start + q * stride;
+#pragma unroll
+      for (int n = 0; n < DIM; ++n) {
+        const double hn = 0.5 * nfv[n] * rv;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) fs[c] = fma(-hn, sF[(n * NC + c) * nq + ii], fs[c]);
+      }
+    }
+    const double bj = __ldg(T.B + j) * Jf;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * NF + j] = bj * fs[c];
+  }
+  __syncthreads();
+  // ---- phase 2: volume terms along the tensor lines + lifting
+  if (active) {
+    double r[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r[c] = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) {
+      constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
+      const int stride = (m == 0) ? s0 : (m == 1 ? s1 : 1);
+      const int am = (i / stride) % N1;
+      const int line0 = tid - am * stride;
+      const double* Dm = sD + m * N1 * N1;
+#pragma unroll
+      for (int b = 0; b < N1; ++b) {
+        const int jt = line0 + b * stride;
+        const double dt = Dm[b * N1 + am];   // D_m[b, a]  (transpose apply)
+        const double dd = Dm[am * N1 + b];   // D_m[a, b]
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          double acc = 0.0;
+#pragma unroll
+          for (int n = 0; n < DIM; ++n) acc = fma(H[m + DIM * n], sF[(n * NC + c) * nq + jt], acc);
+          r[c] = fma(dt, sG[(m * NC + c) * nq + jt], r[c]);
+          r[c] = fma(-dd, acc, r[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
+      const double rv = __ldg(F.Rv + kk * NQ + i);
+      const double* ff = sFf + e * NC * NF + j;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
+  }
+  __syncthreads();
   apply_Vt_t<DIM, N1, NC, EL>(vtab(T), sR, sM, sX);
   mass_solve_t<DIM, N1, NC, EL>(T, G, k0, sM, sR, sX);
   store_result(T, G, rk, k0, EL, NC, sM, dudt);

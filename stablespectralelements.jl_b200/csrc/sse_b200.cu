@@ -69,6 +69,8 @@ struct sse_handle {
   int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
   int const_conflict = 0;
   bool r_ap = false;
+  int fast_std = 0;
+  std::vector<std::vector<double>> S_dense;
 };
 
 template <typename Tp>
@@ -230,6 +232,21 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   return 0;
 }
 
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
+  using Cf = STCfg<DIM, N1, LAW, COLLAPSED, KC>;
+  if (Cf::NF != h->cfg.N_f) return fail("facet-node count does not match the specialised kernel");
+  const size_t smem = Cf::bytes(h->cfg.N_p);
+  CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, COLLAPSED, KC>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
+  k_standard_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, 128, smem, h->stream>>>(
+      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // instantiated (dim, n1, law) combinations of the specialised kernels
 static int fast_a_key(int dim, int n1, int law) {
   if ((dim == 2 || dim == 3) && n1 >= 3 && n1 <= 5 && (law == LAW_EULER || law == LAW_ADV))
@@ -262,6 +279,15 @@ static int run_a(sse_handle* h, const double* u_dev) {
   SSE_DISPATCH(launch_a, h, u_dev);
 }
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
+  switch (h->fast_std) {   // standard form, advection on collapsed simplices
+    case 203: return launch_std_fast<2, 3, LAW_ADV, true, 3>(h, dudt_dev, rk);
+    case 204: return launch_std_fast<2, 4, LAW_ADV, true, 3>(h, dudt_dev, rk);
+    case 205: return launch_std_fast<2, 5, LAW_ADV, true, 3>(h, dudt_dev, rk);
+    case 303: return launch_std_fast<3, 3, LAW_ADV, true, 6>(h, dudt_dev, rk);
+    case 304: return launch_std_fast<3, 4, LAW_ADV, true, 7>(h, dudt_dev, rk);
+    case 305: return launch_std_fast<3, 5, LAW_ADV, true, 8>(h, dudt_dev, rk);
+    default: break;
+  }
   switch (h->fast_b) {
     case 203: return launch_b_fast<2, 3, LAW_EULER, true, 3>(h, dudt_dev, rk);
     case 204: return launch_b_fast<2, 4, LAW_EULER, true, 3>(h, dudt_dev, rk);
@@ -493,7 +519,11 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
           dev_upload_vec(h, A.v, &T.S_v))
         return -1;
 
-      // ---- tensor-product fast path: line-pair tables for S, ELL tables for C = R^T B
+      h->S_dense = S;   // consumed by the tensor-product fast-path setup below
+    }
+    // ---- tensor-product fast paths: ELL tables for C = R^T B / R^T, 1-D derivative matrices,
+    //      and (flux differencing) the line-pair tables of S
+    {
       const int n1 = ops->n1d;
       size_t nd1 = 1;
       for (int m = 0; m < d; ++m) nd1 *= (size_t)std::max(n1, 1);
@@ -502,16 +532,46 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       for (int i = 0; i < Nq; ++i) uniform = uniform && (Rt.rp[i + 1] - Rt.rp[i] == kc);
       const bool collapsed = !Gref.empty();
       bool ok = d >= 2 && n1 >= 2 && (int)nd1 == Nq && uniform && kc > 0 && !cfg->r_is_selection &&
-                !ops->Minv &&
+                !ops->Minv && h->r_ap && Nf < 65536 &&
                 (cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED || cfg->mass_solver == SSE_MASS_DIAGONAL);
+      std::vector<int> stride(d, 1);
+      for (int l = 0; l < d; ++l)
+        for (int q = l + 1; q < d; ++q) stride[l] *= std::max(n1, 1);
+      // D_eta^m must be I (x) D1_m (x) I
+      std::vector<double> D1((size_t)d * n1 * n1, 0.0);
+      for (int m = 0; m < d && ok; ++m) {
+        for (int a = 0; a < n1; ++a)
+          for (int bb = 0; bb < n1; ++bb)
+            D1[((size_t)m * n1 + a) * n1 + bb] = Dd[m][(size_t)(a * stride[m]) * Nq + bb * stride[m]];
+        for (int i = 0; i < Nq && ok; ++i)
+          for (int j = 0; j < Nq && ok; ++j) {
+            int ndiff = 0;
+            for (int l = 0; l < d; ++l)
+              if (l != m && (i / stride[l]) % n1 != (j / stride[l]) % n1) ++ndiff;
+            double expect = ndiff ? 0.0
+                                  : D1[((size_t)m * n1 + (i / stride[m]) % n1) * n1 + (j / stride[m]) % n1];
+            if (Dd[m][(size_t)i * Nq + j] != expect) ok = false;
+          }
+      }
       if (ok) {
+        std::vector<int> Cj((size_t)kc * Nq);
+        std::vector<double> Cvv((size_t)kc * Nq), Rvv((size_t)kc * Nq);
+        for (int i = 0; i < Nq; ++i)
+          for (int q = 0; q < kc; ++q) {
+            int en = Rt.rp[i] + q;
+            Cj[(size_t)q * Nq + i] = Rt.ci[en] | ((Rt.ci[en] / T.npf) << 16);
+            Cvv[(size_t)q * Nq + i] = Cv[en];
+            Rvv[(size_t)q * Nq + i] = Rt.v[en];
+          }
+        if (dev_upload_vec(h, Cj, &h->F.Cj) || dev_upload_vec(h, Cvv, &h->F.Cv) ||
+            dev_upload_vec(h, Rvv, &h->F.Rv) || dev_upload_vec(h, D1, &h->F.D1))
+          return -1;
+        h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
+        h->fast_std = (cfg->form == SSE_FORM_STANDARD) ? 1 : 0;
+      }
+      if (ok && cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
+        const std::vector<std::vector<double>>& S = h->S_dense;
         const int H = n1 / 2;
-        std::vector<int> stride(d);
-        for (int l = 0; l < d; ++l) {
-          int st = 1;
-          for (int q = l + 1; q < d; ++q) st *= n1;
-          stride[l] = st;
-        }
         // every non-zero of S_m must couple two nodes of one tensor line l with an allowed m
         for (int m = 0; m < d && ok; ++m)
           for (int i = 0; i < Nq && ok; ++i)
@@ -533,23 +593,11 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
                 for (int m = 0; m < d; ++m)
                   Sp[(((size_t)l * H + (o - 1)) * d + m) * Nq + i] = S[m][(size_t)i * Nq + j];
               }
-          std::vector<int> Cj((size_t)kc * Nq);
-          std::vector<double> Cvv((size_t)kc * Nq), Rvv((size_t)kc * Nq);
-          for (int i = 0; i < Nq; ++i)
-            for (int q = 0; q < kc; ++q) {
-              int en = Rt.rp[i] + q;
-              Cj[(size_t)q * Nq + i] = Rt.ci[en] | ((Rt.ci[en] / T.npf) << 16);
-              Cvv[(size_t)q * Nq + i] = Cv[en];
-              Rvv[(size_t)q * Nq + i] = Rt.v[en];
-            }
-          if (Nf >= 65536 || !h->r_ap) ok = false;
-          if (ok && (dev_upload_vec(h, Sp, &h->F.Sp) || dev_upload_vec(h, Cj, &h->F.Cj) ||
-                     dev_upload_vec(h, Cvv, &h->F.Cv) || dev_upload_vec(h, Rvv, &h->F.Rv)))
-            return -1;
-          h->fast_b = ok ? 1 : 0;
-          h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
+          if (dev_upload_vec(h, Sp, &h->F.Sp)) return -1;
+          h->fast_b = 1;
         }
       }
+      h->S_dense.clear();
     }
   }
   {
@@ -691,6 +739,12 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
+    if (h->fast_std && !force_generic && law_t == LAW_ADV && h->collapsed && h->n1 >= 3 &&
+        h->n1 <= 5 && cfg->strategy == SSE_REFERENCE_OPERATOR &&
+        ((d == 3 && h->kc == 3 + h->n1) || (d == 2 && h->kc == 3)))
+      h->fast_std = d * 100 + h->n1;
+    else
+      h->fast_std = 0;
   }
   auto smem_a_fast = [&](int E) {
     return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf +
@@ -709,7 +763,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
-  if (h->fast_b) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
+  if (h->fast_b || h->fast_std) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL / STCfg::EL
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
