@@ -699,160 +699,155 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 }
 
 // ============================================ loop B, standard form, reference operators
-// time_derivative! of standard_form_first_order.jl:16-63 on tensor-product elements
-// (skew-symmetric split form; see k_standard_ref for the algebra).  HBM-bound: per element it
-// streams Λ_q (d*d*N_q), J_q, nJf, J_f, the traces and u_q once and writes dudt; everything else
-// lives in shared memory / registers.  D_eta^m = I ⊗ D1[m] ⊗ I acts along tensor lines, with
-// the three 1-D matrices staged in shared memory.
-// shared (doubles): sF[DIM][NC][nq] | sG[DIM][NC][nq] | sFf[EL][NC][NF] | sD[DIM][N1][N1] |
-//                   sR[EL][NC][NQ] | sM[EL][NC][Np] | sX[2*NC*nq]
-template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+// time_derivative! of standard_form_first_order.jl:16-63 on tensor-product simplices, scalar
+// conservation laws (linear advection, Burgers): f_n(u) = a_n φ(u), so the skew-symmetric split
+//   r = Σ_m [ D_m^T (h_m ∘ φ) − h_m ∘ (D_m φ) ],   h_m = ½ W Σ_n Λ_η[m,n] a_n
+// needs one nodal scalar φ and d metric scalars h_m per node.  HBM-bound: each thread owns node
+// i of NB consecutive elements ("elements as components"), so every operator-table read, index
+// computation and barrier is amortised over NB elements while 11*NB independent global loads per
+// thread are in flight.
+// shared (doubles): sPhi[NB][NQ] | sG[DIM][NB][NQ] | sFf[NB][NF] | sD[DIM][N1][N1] |
+//                   sR[NB][NQ] | sM[NB][Np] | sX[2*NB*NQ]
+template <int DIM, int N1, int LAW, int KC, int NB>
 struct STCfg {
-  static constexpr int NC = LawTraits<DIM, LAW>::NC;
   static constexpr int NQ = ipow(N1, DIM);
-  static constexpr int EL = (128 / NQ) > 0 ? 128 / NQ : 1;
-  static constexpr int NF = TensorNF<DIM, N1, COLLAPSED>::value;
-  static constexpr int nq = EL * NQ, nf = EL * NF;
-  static constexpr int oF = 0;
-  static constexpr int oG = oF + DIM * NC * nq;
-  static constexpr int oFf = oG + DIM * NC * nq;
-  static constexpr int oD = oFf + NC * nf;
+  static constexpr int NF = TensorNF<DIM, N1, true>::value;
+  static constexpr int oPhi = 0;
+  static constexpr int oG = oPhi + NB * NQ;
+  static constexpr int oFf = oG + DIM * NB * NQ;
+  static constexpr int oD = oFf + NB * NF;
   static constexpr int oR = oD + DIM * N1 * N1;
-  static __host__ __device__ constexpr int oM() { return oR + NC * nq; }
-  static __host__ __device__ constexpr int oX(int Np) { return oM() + EL * NC * Np; }
+  static __host__ __device__ constexpr int oM() { return oR + NB * NQ; }
+  static __host__ __device__ constexpr int oX(int Np) { return oM() + NB * Np; }
   static __host__ __device__ constexpr size_t bytes(int Np) {
-    return sizeof(double) * (size_t)(oX(Np) + 2 * NC * nq);
+    return sizeof(double) * (size_t)(oX(Np) + 2 * NB * NQ);
   }
 };
 
-template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+template <int DIM, int N1, int LAW, int KC, int NB>
 __global__ void __launch_bounds__(128)
 k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt) {
-  using Cf = STCfg<DIM, N1, LAW, COLLAPSED, KC>;
-  constexpr int NC = Cf::NC, NQ = Cf::NQ, NF = Cf::NF, EL = Cf::EL, nq = Cf::nq, nf = Cf::nf;
-  constexpr int NS = LawTraits<DIM, LAW>::NS;
+  static_assert(LAW != LAW_EULER, "scalar conservation laws only");
+  using Cf = STCfg<DIM, N1, LAW, KC, NB>;
+  constexpr int NQ = Cf::NQ, NF = Cf::NF;
   constexpr int DD = DIM * DIM;
   extern __shared__ __align__(16) double sm[];
   const int Np = T.N_p;
-  double* sF = sm + Cf::oF;
+  double* sPhi = sm + Cf::oPhi;
   double* sG = sm + Cf::oG;
   double* sFf = sm + Cf::oFf;
   double* sD = sm + Cf::oD;
   double* sR = sm + Cf::oR;
   double* sM = sm + Cf::oM();
   double* sX = sm + Cf::oX(Np);
-  const long long k0 = G.k_begin + (long long)blockIdx.x * EL;
+  const long long k0 = G.k_begin + (long long)blockIdx.x * NB;
   const int tid = threadIdx.x;
-  const bool active = tid < nq;
-  const int e = active ? tid / NQ : 0;
-  const int i = active ? tid % NQ : 0;
+  const bool active = tid < NQ;
+  const int i = active ? tid : 0;
 
-  // 1-D derivative matrices (row-major [l][a][b] = D1_l[a][b])
   for (int idx = tid; idx < DIM * N1 * N1; idx += 128) sD[idx] = __ldg(F.D1 + idx);
 
-  double H[DD];   // H[m + DIM*n] = ½ W Λ_η[i, m, n]
-  // ---- phase 0: physical flux, collapsed metrics, g_m = Σ_n H[m][n] f_n
+  double ha[NB][DIM];
+  // ---- phase 0: φ(u) and the metric scalars h_m at the volume nodes
   if (active) {
-    long long k = min(k0 + e, G.N_e - 1);
-    double uu[NC], s[NS], Lq[DD];
+    double uu[NB], Lq[NB][DD];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) uu[c] = __ldcg(u_q + (k * NC + c) * NQ + i);
+    for (int b = 0; b < NB; ++b) {
+      const long long k = min(k0 + b, G.N_e - 1);
+      uu[b] = __ldcg(u_q + k * NQ + i);
 #pragma unroll
-    for (int c = 0; c < DD; ++c) Lq[c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
-    cons_to_state<DIM, LAW>(P, uu, s);
-    const double hw = 0.5 * __ldg(T.W + i);
-#pragma unroll
-    for (int m = 0; m < DIM; ++m)
-#pragma unroll
-      for (int n = 0; n < DIM; ++n) {
-        double v;
-        if constexpr (COLLAPSED) {
-          v = 0.0;
-#pragma unroll
-          for (int l = 0; l < DIM; ++l)
-            if (l >= m)   // Λ_ref is upper triangular in collapsed coordinates
-              v = fma(__ldg(T.Gref + (i * DIM + m) * DIM + l), Lq[l + DIM * n], v);
-        } else {
-          v = Lq[m + DIM * n];
-        }
-        H[m + DIM * n] = hw * v;
-      }
-    double fq[DIM][NC];
-#pragma unroll
-    for (int n = 0; n < DIM; ++n) {
-      double cdir[DIM];
-#pragma unroll
-      for (int m = 0; m < DIM; ++m) cdir[m] = (m == n) ? 1.0 : 0.0;
-      physical_flux_c<DIM, LAW>(P, s, cdir, fq[n]);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) sF[(n * NC + c) * nq + tid] = fq[n][c];
+      for (int c = 0; c < DD; ++c) Lq[b][c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
     }
+    const double hw = 0.5 * __ldg(T.W + i);
+    double gref[DD];
 #pragma unroll
-    for (int m = 0; m < DIM; ++m)
+    for (int c = 0; c < DD; ++c) gref[c] = __ldg(T.Gref + i * DD + c);   // [m][l]
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        double g = 0.0;
+    for (int b = 0; b < NB; ++b) {
+      double la[DIM];   // Σ_n Λ_q[l,n] a_n
 #pragma unroll
-        for (int n = 0; n < DIM; ++n) g = fma(H[m + DIM * n], fq[n][c], g);
-        sG[(m * NC + c) * nq + tid] = g;
+      for (int l = 0; l < DIM; ++l) {
+        double v = 0.0;
+#pragma unroll
+        for (int n = 0; n < DIM; ++n) v = fma(Lq[b][l + DIM * n], P.a[n], v);
+        la[l] = v;
       }
+      const double phi = (LAW == LAW_ADV) ? uu[b] : 0.5 * uu[b] * uu[b];
+      sPhi[b * NQ + i] = phi;
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) {
+        double v = 0.0;
+#pragma unroll
+        for (int l = m; l < DIM; ++l) v = fma(gref[m * DIM + l], la[l], v);   // upper triangular
+        ha[b][m] = hw * v;
+        sG[(m * NB + b) * NQ + i] = ha[b][m] * phi;
+      }
+    }
   }
   __syncthreads();
-  // ---- phase 1: facet nodes: f_f = B J_f (f* − Σ_n ½ n_n (R f_n))
-  for (int idx = tid; idx < nf; idx += 128) {
-    const int j = idx % NF, ee = idx / NF;
-    long long k = min(k0 + ee, G.N_e - 1);
-    long long gj = k * NF + j;
-    double nfv[DIM], sl[NS], fs[NC];
+  // ---- phase 1: facet nodes: f_f = B J_f (f* − ½ (a·n) (R φ))
+  for (int idx = tid; idx < NB * NF; idx += 128) {
+    const int j = idx % NF, b = idx / NF;
+    const long long k = min(k0 + b, G.N_e - 1);
+    const long long gj = k * NF + j;
+    double nfv[DIM], sl[2], fs[1];
     const double Jf = __ldcg(G.J_f + gj);
     const int ext = __ldcg(G.toff + gj);
     const double iJf = frcp(Jf);
+    double an = 0.0;
 #pragma unroll
-    for (int m = 0; m < DIM; ++m) nfv[m] = __ldcg(G.nJf + gj * DIM + m) * iJf;
-    interface_flux<DIM, LAW>(P, 0, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
-    const int b = __ldg(T.R_rp + j);
+    for (int m = 0; m < DIM; ++m) {
+      nfv[m] = __ldcg(G.nJf + gj * DIM + m) * iJf;
+      an = fma(P.a[m], nfv[m], an);
+    }
+    interface_flux<DIM, LAW>(P, 0, u_f, k * NF + j, ext, NF, nfv, sl, fs);
+    const int rb = __ldg(T.R_rp + j);
     const int desc = __ldg(T.R_desc + j);
     const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
-    for (int q = 0; q < cnt; ++q) {
-      const double rv = __ldg(T.R_v + b + q);
-      const int ii = ee * NQ + start + q * stride;
+    const double* ph = sPhi + b * NQ + start;
+    double rphi = 0.0;
+    if (cnt == N1) {
 #pragma unroll
-      for (int n = 0; n < DIM; ++n) {
-        const double hn = 0.5 * nfv[n] * rv;
+      for (int q = 0; q < N1; ++q) rphi = fma(__ldg(T.R_v + rb + q), ph[q * stride], rphi);
+    } else if (cnt == N1 * N1 && stride == 1) {
+      double part[N1];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) fs[c] = fma(-hn, sF[(n * NC + c) * nq + ii], fs[c]);
+      for (int q2 = 0; q2 < N1; ++q2) {
+        part[q2] = 0.0;
+#pragma unroll
+        for (int q = 0; q < N1; ++q)
+          part[q2] = fma(__ldg(T.R_v + rb + q2 * N1 + q), ph[q2 * N1 + q], part[q2]);
       }
-    }
-    const double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * NF + j] = bj * fs[c];
+      for (int q2 = 0; q2 < N1; ++q2) rphi += part[q2];
+    } else {
+      for (int q = 0; q < cnt; ++q) rphi = fma(__ldg(T.R_v + rb + q), ph[q * stride], rphi);
+    }
+    sFf[b * NF + j] = __ldg(T.B + j) * Jf * fma(-0.5 * an, rphi, fs[0]);
   }
   __syncthreads();
   // ---- phase 2: volume terms along the tensor lines + lifting
   if (active) {
-    double r[NC];
+    double r[NB];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) r[c] = 0.0;
+    for (int b = 0; b < NB; ++b) r[b] = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) {
       constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
       const int stride = (m == 0) ? s0 : (m == 1 ? s1 : 1);
       const int am = (i / stride) % N1;
-      const int line0 = tid - am * stride;
+      const int line0 = i - am * stride;
       const double* Dm = sD + m * N1 * N1;
 #pragma unroll
-      for (int b = 0; b < N1; ++b) {
-        const int jt = line0 + b * stride;
-        const double dt = Dm[b * N1 + am];   // D_m[b, a]  (transpose apply)
-        const double dd = Dm[am * N1 + b];   // D_m[a, b]
+      for (int q = 0; q < N1; ++q) {
+        const int jt = line0 + q * stride;
+        const double dt = Dm[q * N1 + am];   // D_m[q, a]  (transpose apply)
+        const double dd = Dm[am * N1 + q];   // D_m[a, q]
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          double acc = 0.0;
-#pragma unroll
-          for (int n = 0; n < DIM; ++n) acc = fma(H[m + DIM * n], sF[(n * NC + c) * nq + jt], acc);
-          r[c] = fma(dt, sG[(m * NC + c) * nq + jt], r[c]);
-          r[c] = fma(-dd, acc, r[c]);
+        for (int b = 0; b < NB; ++b) {
+          r[b] = fma(dt, sG[(m * NB + b) * NQ + jt], r[b]);
+          r[b] = fma(-dd * ha[b][m], sPhi[b * NQ + jt], r[b]);
         }
       }
     }
@@ -860,17 +855,33 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     for (int kk = 0; kk < KC; ++kk) {
       const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
       const double rv = __ldg(F.Rv + kk * NQ + i);
-      const double* ff = sFf + e * NC * NF + j;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
+      for (int b = 0; b < NB; ++b) r[b] = fma(-rv, sFf[b * NF + j], r[b]);
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
+    for (int b = 0; b < NB; ++b) sR[b * NQ + i] = r[b];
   }
   __syncthreads();
-  apply_Vt_t<DIM, N1, NC, EL>(vtab(T), sR, sM, sX);
-  mass_solve_t<DIM, N1, NC, EL>(T, G, k0, sM, sR, sX);
-  store_result(T, G, rk, k0, EL, NC, sM, dudt);
+  // ---- phase 3: dudt = M^-1 V^T r  (the NB elements ride along as NB "components")
+  apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
+  if (T.mass_kind == MASS_DIAGONAL) {
+    SSE_LOOP(idx, NB * NQ) {
+      const int ii = idx % NQ, b = idx / NQ;
+      const long long k = min(k0 + b, G.N_e - 1);
+      sM[idx] = fdiv(sM[idx], __ldg(T.W + ii) * __ldcg(G.J_q + k * NQ + ii));
+    }
+    __syncthreads();
+  } else {
+    apply_V_t<DIM, N1, NB, 1>(vtab(T), sM, sR, sX);
+    SSE_LOOP(idx, NB * NQ) {
+      const int ii = idx % NQ, b = idx / NQ;
+      const long long k = min(k0 + b, G.N_e - 1);
+      sR[idx] *= fdiv(__ldg(T.W + ii), __ldcg(G.J_q + k * NQ + ii));
+    }
+    __syncthreads();
+    apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
+  }
+  store_result(T, G, rk, k0, NB, 1, sM, dudt);
 }
 
 }  // namespace sse

@@ -232,15 +232,15 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   return 0;
 }
 
-template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+template <int DIM, int N1, int LAW, int KC, int NB>
 static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
-  using Cf = STCfg<DIM, N1, LAW, COLLAPSED, KC>;
+  using Cf = STCfg<DIM, N1, LAW, KC, NB>;
   if (Cf::NF != h->cfg.N_f) return fail("facet-node count does not match the specialised kernel");
   const size_t smem = Cf::bytes(h->cfg.N_p);
-  CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, COLLAPSED, KC>,
+  CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, KC, NB>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
-  k_standard_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, 128, smem, h->stream>>>(
+  int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
+  k_standard_tensor<DIM, N1, LAW, KC, NB><<<grid, 128, smem, h->stream>>>(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
   CU(cudaGetLastError());
@@ -280,12 +280,9 @@ static int run_a(sse_handle* h, const double* u_dev) {
 }
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
   switch (h->fast_std) {   // standard form, advection on collapsed simplices
-    case 203: return launch_std_fast<2, 3, LAW_ADV, true, 3>(h, dudt_dev, rk);
-    case 204: return launch_std_fast<2, 4, LAW_ADV, true, 3>(h, dudt_dev, rk);
-    case 205: return launch_std_fast<2, 5, LAW_ADV, true, 3>(h, dudt_dev, rk);
-    case 303: return launch_std_fast<3, 3, LAW_ADV, true, 6>(h, dudt_dev, rk);
-    case 304: return launch_std_fast<3, 4, LAW_ADV, true, 7>(h, dudt_dev, rk);
-    case 305: return launch_std_fast<3, 5, LAW_ADV, true, 8>(h, dudt_dev, rk);
+    case 303: return launch_std_fast<3, 3, LAW_ADV, 6, 4>(h, dudt_dev, rk);
+    case 304: return launch_std_fast<3, 4, LAW_ADV, 7, 4>(h, dudt_dev, rk);
+    case 305: return launch_std_fast<3, 5, LAW_ADV, 8, 4>(h, dudt_dev, rk);
     default: break;
   }
   switch (h->fast_b) {
@@ -741,7 +738,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = 0;
     if (h->fast_std && !force_generic && law_t == LAW_ADV && h->collapsed && h->n1 >= 3 &&
         h->n1 <= 5 && cfg->strategy == SSE_REFERENCE_OPERATOR &&
-        ((d == 3 && h->kc == 3 + h->n1) || (d == 2 && h->kc == 3)))
+        d == 3 && h->kc == 3 + h->n1)
       h->fast_std = d * 100 + h->n1;
     else
       h->fast_std = 0;
@@ -763,7 +760,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
-  if (h->fast_b || h->fast_std) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL / STCfg::EL
+  if (h->fast_b) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
+  if (h->fast_std) h->E_b = 4;                        // STCfg NB
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
