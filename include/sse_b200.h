@@ -150,6 +150,12 @@ int sse_halo_pack(sse_handle* h);      /* traces -> send buffer (after sse_nodal
 int sse_halo_unpack(sse_handle* h);    /* recv buffer -> halo trace slots                     */
 
 /* Streams / timing / introspection. */
+/* Host-buffer building blocks for element-sharded runs: chunked H2D of u overlapped with loop A
+ * (returns without synchronising); D2H of dudt for an element range, ordered after the work
+ * already queued, on the handle's copy stream; sse_sync_copies waits for the copies. */
+int sse_upload_and_nodal_values(sse_handle* h, const double* u_host);
+int sse_download_dudt_range(sse_handle* h, double* dudt_host, int64_t k_begin, int64_t k_end);
+int sse_sync_copies(sse_handle* h);
 /* Asynchronous (stream-ordered) H2D of the state / D2H of dudt (the latter synchronises). */
 int sse_upload_state(sse_handle* h, const double* u_host);
 int sse_download_dudt(sse_handle* h, double* dudt_host);

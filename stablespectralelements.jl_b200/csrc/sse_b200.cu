@@ -41,6 +41,8 @@ static int fail(const char* fmt, ...) {
                   cudaGetErrorString(e_));                                            \
   } while (0)
 
+#define SSE_MAX_CHUNKS 16
+
 struct sse_handle {
   sse_config cfg{};
   Tables T{};
@@ -48,6 +50,9 @@ struct sse_handle {
   Phys P{};
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[SSE_MAX_CHUNKS] = {};
+  unsigned next_ev = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> allocs;
   int64_t bytes = 0;
@@ -311,6 +316,9 @@ int sse_destroy(sse_handle* h) {
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto& e : h->ev_chunk)
+    if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -347,6 +355,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
 
   CU(cudaSetDevice(cfg->device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
 
   Tables& T = h->T;
@@ -808,11 +818,97 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
     if (run_a(h, u)) return -1;
     return run_b(h, dudt, rk);
   }
-  CU(cudaMemcpyAsync(h->u, u, h->n_state * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (run_a(h, h->u)) return -1;
-  if (run_b(h, h->dudt, rk)) return -1;
-  CU(cudaMemcpyAsync(dudt, h->dudt, h->n_state * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  // Host buffers: pipeline the copies against the kernels in element chunks.  Loop A of chunk c
+  // starts as soon as its slice of u has landed; loop B needs every trace, so it starts after
+  // the last loop A and its chunks are copied back while later chunks still compute.
+  // (Asynchronous only for pinned host memory; pageable memory degrades to staged copies.)
+  const int64_t Ne = h->cfg.N_e;
+  const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
+  int nchunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+  if (h->second_order) nchunk = 1;
+  auto lo = [&](int c) { return (Ne * c) / nchunk; };
+  for (int c = 0; c < nchunk; ++c) {
+    CU(cudaMemcpyAsync(h->u + lo(c) * blk, u + lo(c) * blk, (lo(c + 1) - lo(c)) * blk * sizeof(double),
+                       cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
+  }
+  int rc = 0;
+  for (int c = 0; c < nchunk && !rc; ++c) {
+    CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
+    h->G.k_begin = lo(c);
+    h->G.N_e = lo(c + 1);
+    rc = run_a(h, h->u);
+  }
+  for (int c = 0; c < nchunk && !rc; ++c) {
+    h->G.k_begin = lo(c);
+    h->G.N_e = lo(c + 1);
+    rc = run_b(h, h->dudt, rk);
+    if (rc) break;
+    CU(cudaEventRecord(h->ev_chunk[c], h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[c], 0));
+    CU(cudaMemcpyAsync(dudt + lo(c) * blk, h->dudt + lo(c) * blk,
+                       (lo(c + 1) - lo(c)) * blk * sizeof(double), cudaMemcpyDeviceToHost,
+                       h->copy_stream));
+  }
+  h->G.k_begin = 0;
+  h->G.N_e = Ne;
+  if (rc) return -1;
+  CU(cudaStreamSynchronize(h->copy_stream));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Host-buffer building blocks for element-sharded runs (the host framework issues the halo
+// exchange between them): chunked H2D of u overlapped with loop A ...
+int sse_upload_and_nodal_values(sse_handle* h, const double* u_host) {
+  if (!h || !u_host) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t Ne = h->cfg.N_e;
+  const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
+  const int nchunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+  auto lo = [&](int c) { return (Ne * c) / nchunk; };
+  // the copy stream must not overwrite u while earlier work of the main stream still reads it
+  CU(cudaEventRecord(h->ev[3], h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev[3], 0));
+  for (int c = 0; c < nchunk; ++c) {
+    CU(cudaMemcpyAsync(h->u + lo(c) * blk, u_host + lo(c) * blk,
+                       (lo(c + 1) - lo(c)) * blk * sizeof(double), cudaMemcpyHostToDevice,
+                       h->copy_stream));
+    CU(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
+  }
+  int rc = 0;
+  for (int c = 0; c < nchunk && !rc; ++c) {
+    CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
+    h->G.k_begin = lo(c);
+    h->G.N_e = lo(c + 1);
+    rc = run_a(h, h->u);
+  }
+  h->G.k_begin = 0;
+  h->G.N_e = Ne;
+  return rc;
+}
+
+// ... and D2H of dudt for the element range [k_begin, k_end), ordered after the work already
+// queued on the main stream, on the copy stream (sse_sync_copies waits for all of them).
+int sse_download_dudt_range(sse_handle* h, double* dudt_host, int64_t k_begin, int64_t k_end) {
+  if (!h || !dudt_host) return fail("null argument");
+  if (k_begin < 0 || k_end > h->cfg.N_e || k_begin > k_end) return fail("bad element range");
+  if (k_begin == k_end) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
+  cudaEvent_t ev = h->ev_chunk[h->next_ev++ % SSE_MAX_CHUNKS];
+  CU(cudaEventRecord(ev, h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, ev, 0));
+  CU(cudaMemcpyAsync(dudt_host + k_begin * blk, h->dudt + k_begin * blk,
+                     (k_end - k_begin) * blk * sizeof(double), cudaMemcpyDeviceToHost,
+                     h->copy_stream));
+  return 0;
+}
+
+int sse_sync_copies(sse_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->copy_stream));
   return 0;
 }
 

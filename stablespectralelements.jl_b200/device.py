@@ -60,7 +60,8 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_halo_buffers", "sse_halo_pack", "sse_halo_unpack", "sse_sync", "sse_stream",
            "sse_time_residual", "sse_kernel_launches", "sse_device_bytes",
            "sse_measure_fp64_peak", "sse_time_derivative_range", "sse_set_stream",
-           "sse_upload_state", "sse_download_dudt"]
+           "sse_upload_state", "sse_download_dudt", "sse_upload_and_nodal_values",
+           "sse_download_dudt_range", "sse_sync_copies"]
 
 
 def load_library(path: Optional[str] = None):
@@ -104,6 +105,9 @@ def load_library(path: Optional[str] = None):
     lib.sse_set_stream.argtypes = [vp, vp]
     lib.sse_upload_state.argtypes = [vp, vp]
     lib.sse_download_dudt.argtypes = [vp, vp]
+    lib.sse_upload_and_nodal_values.argtypes = [vp, vp]
+    lib.sse_download_dudt_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    lib.sse_sync_copies.argtypes = [vp]
     if path is None:
         _LIB = lib
     return lib
@@ -339,6 +343,19 @@ class DeviceResidual:
     def download_dudt(self, dudt: np.ndarray):
         assert dudt.shape == self.shape and dudt.dtype == np.float64 and dudt.flags.c_contiguous
         self._check(self.lib.sse_download_dudt(self.h, dudt.ctypes.data), "sse_download_dudt")
+
+    def upload_and_nodal_values(self, u: np.ndarray):
+        assert u.shape == self.shape and u.dtype == np.float64 and u.flags.c_contiguous
+        self._check(self.lib.sse_upload_and_nodal_values(self.h, u.ctypes.data),
+                    "sse_upload_and_nodal_values")
+
+    def download_dudt_range(self, dudt: np.ndarray, k_begin: int, k_end: int):
+        assert dudt.shape == self.shape and dudt.dtype == np.float64 and dudt.flags.c_contiguous
+        self._check(self.lib.sse_download_dudt_range(self.h, dudt.ctypes.data, k_begin, k_end),
+                    "sse_download_dudt_range")
+
+    def sync_copies(self):
+        self._check(self.lib.sse_sync_copies(self.h), "sse_sync_copies")
 
     def set_state(self, u: np.ndarray):
         u = _f64(u)

@@ -165,21 +165,29 @@ class DistributedResidual:
             ro += nr
         return ops
 
-    def _exchange_and_time_derivative(self):
+    def _exchange_and_time_derivative(self, dudt_host=None):
+        """Halo exchange + loop B.  With ``dudt_host`` the result is copied back range by range
+        while later ranges still compute (the interior is cut into a few pieces for that)."""
         import torch.distributed as dist
         d = self.dev
         d.halo_pack()
         works = dist.batch_isend_irecv(self._p2p_ops())
         k_lo, k_hi = self.part.interior
-        if k_hi > k_lo:
-            d.time_derivative_range(k_lo, k_hi)        # overlaps the NVLink transfer
+        if k_hi > k_lo:                                    # overlaps the NVLink transfer
+            npieces = 6 if (dudt_host is not None and k_hi - k_lo >= 6 * 4096) else 1
+            cuts = [k_lo + ((k_hi - k_lo) * q) // npieces for q in range(npieces + 1)]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                d.time_derivative_range(a, b)
+                if dudt_host is not None:
+                    d.download_dudt_range(dudt_host, a, b)
         for w in works:
             w.wait()
         d.halo_unpack()
-        if k_lo > 0:
-            d.time_derivative_range(0, k_lo)
-        if k_hi < d.N_e:
-            d.time_derivative_range(max(k_hi, k_lo), d.N_e)
+        for a, b in ((0, k_lo), (max(k_hi, k_lo), d.N_e)):
+            if b > a:
+                d.time_derivative_range(a, b)
+                if dudt_host is not None:
+                    d.download_dudt_range(dudt_host, a, b)
 
     def residual(self):
         """One residual of the device-resident state (dudt stays on the device)."""
@@ -195,9 +203,9 @@ class DistributedResidual:
         if self.world == 1:
             self.dev.residual_host(u, dudt)
             return
-        self.dev.upload_state(u)
-        self.residual()
-        self.dev.download_dudt(dudt)
+        self.dev.upload_and_nodal_values(u)          # chunked H2D overlapped with loop A
+        self._exchange_and_time_derivative(dudt)     # loop B overlapped with the D2H copies
+        self.dev.sync_copies()
 
     def timed_residuals(self, steps: int) -> float:
         """Milliseconds for ``steps`` residuals, CUDA events on the launching stream."""
