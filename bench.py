@@ -33,6 +33,9 @@ import numpy as np  # noqa: E402
 # algorithmic work per element, Tet p=4 Euler flux differencing
 FLOP_PER_ELT = {"loop_b": 133.5e3 + 221.0e3, "loop_a": 75.0e3, "residual": 430.0e3}
 BYTES_PER_ELT_LOOP_B = 8 * (625 + 1125 + 125 + 300 + 100 + 500 + 500 + 175) + 4 * 100
+# dram__bytes_read.sum + dram__bytes_write.sum of the loop-B kernel per element, from the
+# `ncu --set full` capture at M=16 (profiles/r1_fluxdiff_tensor_v8.md): 591.8 MB / 24 576
+TRAFFIC_PER_ELT_LOOP_B = 24080.0
 
 
 def read_peaks():
@@ -244,10 +247,13 @@ def main():
                 "setup_s": round(t_setup, 1),
             },
             "roofline": {
-                "kernel": "k_fluxdiff<3,Euler> (loop B: interface flux + volume flux differencing "
-                          "+ facet correction + lift + mass solve)",
+                "kernel": "k_fluxdiff_tensor<3,5,Euler,collapsed,8> (loop B: interface flux + "
+                          "volume flux differencing + facet correction + lift + mass solve)",
                 "bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": hbm_ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": hbm_ach / peaks["hbm_gbs"],
+                "traffic": TRAFFIC_PER_ELT_LOOP_B * n_loc_e, "traffic_unit": "bytes/launch",
+                "traffic_source": "ncu --set full at M=16, scaled per element",
+                "peak_source": peak_src,
                 "note": "this kernel is FP64-pipe bound by design (AI ~ 12 flop/B); see roofline_fp64",
             },
             "roofline_fp64": {
