@@ -438,6 +438,19 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 // Compile-time geometry of the specialised loop-B kernel: EL elements per 128-thread CTA,
 // NF facet nodes, and the shared-memory carve-up (in doubles; regions holding double2 start
 // on even offsets).
+// Occupancy knobs of the specialised loop-B kernel: minimum resident CTAs per SM (register
+// cap = 65536 / (128 * SSE_FD_MINB)), ELL slots exchanged per facet-correction part, and
+// single- vs double-buffered pair exchange (1 = single buffer + one more barrier per direction).
+#ifndef SSE_FD_MINB
+#define SSE_FD_MINB 4
+#endif
+#ifndef SSE_FD_KQ
+#define SSE_FD_KQ 0      // 0: two halves (ceil(KC/2) slots per part)
+#endif
+#ifndef SSE_FD_SINGLE_BUF
+#define SSE_FD_SINGLE_BUF 0
+#endif
+
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
 struct FDCfg {
   static constexpr int NC = LawTraits<DIM, LAW>::NC;
@@ -448,7 +461,9 @@ struct FDCfg {
   static constexpr int NF = COLLAPSED ? (DIM == 3 ? 4 * N1 * N1 : 3 * N1)
                                       : 2 * DIM * ipow(N1, DIM - 1);
   static constexpr int H = N1 / 2;
-  static constexpr int KH = (KC + 1) / 2;
+  static constexpr int KH = SSE_FD_KQ > 0 ? SSE_FD_KQ : (KC + 1) / 2;   // slots per part
+  static constexpr int NPART = (KC + KH - 1) / KH;
+  static constexpr int NBUF = SSE_FD_SINGLE_BUF ? 1 : 2;
   static constexpr int nq = EL * NQ, nf = EL * NF;
   static __host__ __device__ constexpr int ev(int n) { return (n + 1) & ~1; }
   static constexpr int oS = 0;                                   // double2 [NS2][nq]
@@ -462,7 +477,7 @@ struct FDCfg {
   static constexpr int oM = oR + ev(NC * nq);                    // double  [EL][NC][Np]
   static constexpr int oEnd = oFf + ev(NC * nf);
   static __host__ __device__ constexpr int xmax(int a, int b) { return a > b ? a : b; }
-  static constexpr int sX = xmax(xmax(2 * H * NC, KH * NC), 2 * NC) * nq;
+  static constexpr int sX = xmax(xmax(NBUF * H * NC, KH * NC), 2 * NC) * nq;
   static __host__ __device__ constexpr int oX(int Np) {
     return xmax(oEnd, oM + ev(EL * NC * Np));
   }
@@ -470,7 +485,7 @@ struct FDCfg {
 };
 
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, SSE_FD_MINB)
 k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt) {
   using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
@@ -548,7 +563,8 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
     const int stride = (l == 0) ? s0 : (l == 1 ? s1 : 1);
     const int al = (i / stride) % N1;
-    double* buf = sX + (l & 1) * (H * NC * nq);
+    double* buf = sX + (Cf::NBUF == 2 ? (l & 1) : 0) * (H * NC * nq);
+    if (Cf::NBUF == 1 && l > 0) __syncthreads();   // previous direction's reads are done
     if (active) {
 #pragma unroll
       for (int o = 1; o <= H; ++o) {
@@ -610,10 +626,10 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phases 3/4: facet correction (ELL rows of C = R^T B), exchanged in two halves
   if (!T.r_is_selection) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      __syncthreads();   // previous users of sX (pair buffers / first half) are done
+    for (int half = 0; half < Cf::NPART; ++half) {
+      __syncthreads();   // previous users of sX (pair buffers / previous part) are done
       if (active) {
-        const int kend = (half == 0 ? KH : KC);
+        const int kend = (half + 1) * KH < KC ? (half + 1) * KH : KC;
         // software-pipelined table reads: slot kk+1 is fetched while slot kk is evaluated
         int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node | face << 16
         double cij = __ldg(F.Cv + (half * KH) * NQ + i);
@@ -659,7 +675,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
         const int j = ej % NF, ee = ej / NF;
         const int desc = __ldg(T.R_desc + j);
         const int kslot = (desc >> 27) & 31;
-        if ((half == 0) == (kslot < KH)) {
+        if (kslot / KH == half) {
           const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
           const double* base = sX + ((kslot - half * KH) * NC + c) * nq + ee * NQ + start;
           double acc = 0.0;

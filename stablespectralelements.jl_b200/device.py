@@ -69,7 +69,7 @@ def load_library(path: Optional[str] = None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    p = path or LIB_PATH
+    p = path or os.environ.get("SSE_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: run `python -c 'import __graft_entry__ as g; "
                            f"g.build()'` first -- the residual has no CPU fallback")

@@ -109,3 +109,31 @@ def advection_diffusion_case(d=1, p=4, M=4, lazy=True):
                         LaxFriedrichsNumericalFlux(), BR1())
     solver = Solver(law, sd, form, PhysicalOperator(), lazy=lazy)
     return solver, project_function(InitialDataSine(1.0, (2 * math.pi,) * d), sd)
+
+
+def euler_hex_case(p=3, M=2, lazy=True, interface="ec"):
+    """SURVEY §8(f) item 4 / runtests.jl:131-144: 3-D Euler on curved hexahedra, NodalTensor LGL
+    collocation (diag-E: SelectionMap R, no facet correction), conservative-curl metrics."""
+    g = 1.4
+    law = EulerEquations(3, g)
+    L = 2.0
+    ra = make_reference_approximation(NodalTensor(p), Hex(), mapping_degree=p)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, L),) * 3, (M,) * 3), ra,
+                     ChanWarping(1 / 16, (L, L, L)))
+    sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
+    flux = LaxFriedrichsNumericalFlux() if interface == "lf" else EntropyConservativeNumericalFlux()
+    solver = Solver(law, sd, FluxDifferencingForm(inviscid_numerical_flux=flux),
+                    ReferenceOperator(), lazy=lazy)
+    return solver, project_function(EulerPeriodicTest(3, g, 0.2, L), sd)
+
+
+def burgers_tri_case(p=3, M=3, lazy=True):
+    """2-D inviscid Burgers, flux differencing with the EC flux on curved triangles."""
+    law = InviscidBurgersEquation((1.0, 0.5))
+    ra = make_reference_approximation(ModalTensor(p), Tri(), mapping_degree=p)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M)), ra, 0.1)
+    sd = make_spatial_discretization(mesh, ra)
+    form = FluxDifferencingForm(inviscid_numerical_flux=EntropyConservativeNumericalFlux())
+    solver = Solver(law, sd, form, ReferenceOperator(), lazy=lazy)
+    u0 = project_function(InitialDataSine(1.0, (2 * math.pi,) * 2), sd)
+    return solver, u0 + 1.5

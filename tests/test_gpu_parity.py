@@ -62,6 +62,8 @@ CASES = {
     "euler3d_tet_p3_periodic": lambda: cases.euler_tet_case(p=3, M=2, lazy=False, warp=True,
                                                             ic="periodic"),
     "euler3d_tet_p2_nodal": lambda: cases.euler_tet_case(p=2, M=2, lazy=False, approx="nodal"),
+    "euler3d_hex_nodal_p3_ec": lambda: cases.euler_hex_case(p=3, M=2, lazy=False),
+    "burgers2d_tri_p3_ec": lambda: cases.burgers_tri_case(p=3, M=3, lazy=False),
     "advdiff1d_p4": lambda: cases.advection_diffusion_case(d=1, p=4, M=4, lazy=False),
     "advdiff1d_p8": lambda: cases.advection_diffusion_case(d=1, p=8, M=5, lazy=False),
     "advdiff2d_p3": lambda: cases.advection_diffusion_case(d=2, p=3, M=3, lazy=False),
