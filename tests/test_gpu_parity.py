@@ -127,6 +127,26 @@ def test_fused_rk_matches_host_integration():
         solver.close()
 
 
+def test_device_resident_solve_reproduces_reference_golden_l2():
+    """solve(ode, CarpenterKennedy2N54(), dt) entirely on the device reproduces the reference's
+    golden L2 errors (runtests.jl:14-36 advection-diffusion BR1; :89-96 Euler 1-D Gauss)."""
+    from sse_b200.solvers import ODEProblem, semi_discrete_residual as f
+    from sse_b200.time_integration import CarpenterKennedy2N54, solve
+    for case in (gc.advection_diffusion_1d, gc.euler_1d_gauss):
+        solver, u0, T, dt, exact, gold = case(lazy=False)
+        try:
+            snaps = []
+            u = solve(ODEProblem(f, u0, (0.0, T), solver), CarpenterKennedy2N54(), dt=dt,
+                      save_every=50, callback=lambda uu, t, s: snaps.append(t))
+            prob = oracle_problem(solver)
+            xq = tuple(x.T for x in solver.spatial_discretization.mesh.xyzq)
+            l2 = oc.l2_error(prob, u, np.stack(exact(*xq, T), axis=-1))
+            assert np.max(np.abs(l2 - np.array(gold))) < 1e-10, (l2, gold)
+            assert len(snaps) >= 2 and abs(snaps[-1] - T) < 1e-12
+        finally:
+            solver.close()
+
+
 def test_error_paths():
     solver, u0 = cases.advection_tri_case(p=2, M=2, lazy=False)
     try:
