@@ -363,14 +363,31 @@ struct TensorNF {
                                          : 2 * DIM * ipow(N1, DIM - 1);
 };
 
-// shared: bufP[E*NC*N_p] | bufQ[E*NC*NQ] | bufQ2[E*NC*NQ] | bufF[E*NC*N_f] | tmp[2*E*NC*NQ]
+// Elements per CTA of the loop-A kernel.  NBAT > 1 batches consecutive elements as extra
+// "components" of the same thread in the V / V^T / R applies (every table entry, index
+// computation and barrier then serves NBAT*N_c FMAs).  Measured on B200 for Tet p=4 Euler:
+// NBAT = 2 is 10 % SLOWER (9.53 vs 8.65 ms / 511 k elements) because the doubled shared-memory
+// footprint halves the resident CTAs -- so it stays off for systems (it pays for scalar laws,
+// see k_standard_tensor).
+template <int DIM, int N1>
+struct NodalCfg {
+  static constexpr int NQ = ipow(N1, DIM);
+  static constexpr int E = (128 / NQ) > 0 ? 128 / NQ : 1;
+  static constexpr int NBAT = 1;
+  static constexpr int ET = E * NBAT;     // elements per CTA
+};
+
+// shared: bufP[ET*NC*N_p] | bufQ[ET*NC*NQ] | bufQ2[ET*NC*NQ] | bufF[ET*NC*N_f] | tmp[2*ET*NC*NQ]
 template <int DIM, int N1, int LAW, bool COLLAPSED>
 __global__ void __launch_bounds__(128)
 k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
                double* __restrict__ u_f, int proj) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NQ = ipow(N1, DIM);
-  constexpr int E = (128 / NQ) > 0 ? 128 / NQ : 1;
+  using Cf = NodalCfg<DIM, N1>;
+  constexpr int E = Cf::ET;                 // elements per CTA (pointwise loops, buffers)
+  constexpr int EA = Cf::E;                 // "element" count seen by the applies ...
+  constexpr int NCA = NC * Cf::NBAT;        // ... with NBAT elements folded into the components
   constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
   extern __shared__ __align__(16) double sm[];
   const int Np = T.N_p;
@@ -384,9 +401,9 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 
   SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? __ldcg(u + k0 * NC * Np + idx) : 1.0;
   __syncthreads();
-  apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
+  apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
-    apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
+    apply_R_t<NQ, NCA, EA, Nf, N1>(T, bufQ, bufF);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
     SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
     return;
@@ -407,11 +424,30 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   }
   __syncthreads();
   if (proj == 2) {
-    apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ2, bufP, tmp);
-    mass_solve_t<DIM, N1, NC, E>(T, G, k0, bufP, bufQ2, tmp);
-    apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ2, tmp);
+    apply_Vt_t<DIM, N1, NCA, EA>(vtab(T), bufQ2, bufP, tmp);
+    // mass solve (weight-adjusted, M^-1 = I): V, W/J, V^T -- or the diagonal scaling
+    if (T.mass_kind == MASS_DIAGONAL) {
+      SSE_LOOP(idx, E * NC * NQ) {
+        int i = idx % NQ, e = idx / (NQ * NC);
+        long long k = min(k0 + e, G.N_e - 1);
+        bufP[idx] = fdiv(bufP[idx], __ldg(T.W + i) * __ldcg(G.J_q + k * NQ + i));
+      }
+      __syncthreads();
+    } else {
+      apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ2, tmp);
+      SSE_LOOP(idx, E * NQ) {
+        int i = idx % NQ, e = idx / NQ;
+        long long k = min(k0 + e, G.N_e - 1);
+        double sc = fdiv(__ldg(T.W + i), __ldcg(G.J_q + k * NQ + i));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) bufQ2[(e * NC + c) * NQ + i] *= sc;
+      }
+      __syncthreads();
+      apply_Vt_t<DIM, N1, NCA, EA>(vtab(T), bufQ2, bufP, tmp);
+    }
+    apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ2, tmp);
   }
-  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ2, bufF);
+  apply_R_t<NQ, NCA, EA, Nf, N1>(T, bufQ2, bufF);
   if (proj != 2) {
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
   }

@@ -206,7 +206,7 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
 template <int DIM, int N1, int LAW>
 static int launch_a_fast(sse_handle* h, const double* u_dev) {
   constexpr int NQ = ipow(N1, DIM);
-  constexpr int EL = (128 / NQ) > 0 ? 128 / NQ : 1;
+  constexpr int EL = NodalCfg<DIM, N1>::ET;
   if (TensorNF<DIM, N1, true>::value != h->cfg.N_f)
     return fail("facet-node count does not match the specialised kernel");
   const int Nc = h->cfg.N_c;
