@@ -393,19 +393,14 @@ k_nodal_values(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 // Interface flux at one facet node: f* = F(u-,u+).n [+ halfλ a (u- - u+)]
 // (ConservationLaws.jl:75-128).  Returns the exterior-trace-based flux in fs, the interior
 // state in sl.
+// interface flux from already-loaded interior/exterior conservative traces
 template <int DIM, int LAW>
-__device__ __forceinline__ void interface_flux(const Phys& P, int two_point,
-                                               const double* __restrict__ u_f, long long own,
-                                               long long ext, int stride, const double* nf,
-                                               double* sl, double* fs) {
+__device__ __forceinline__ void interface_flux_vals(const Phys& P, int two_point,
+                                                    const double* um, const double* up,
+                                                    const double* nf, double* sl, double* fs) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NS = LawTraits<DIM, LAW>::NS;
-  double um[NC], up[NC], sr[NS];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    um[c] = __ldcg(u_f + own + (long long)c * stride);
-    up[c] = __ldcg(u_f + ext + (long long)c * stride);
-  }
+  double sr[NS];
   cons_to_state<DIM, LAW>(P, um, sl);
   cons_to_state<DIM, LAW>(P, up, sr);
   two_point_flux_c<DIM, LAW>(P, two_point, sl, sr, nf, fs);
@@ -414,6 +409,21 @@ __device__ __forceinline__ void interface_flux(const Phys& P, int two_point,
 #pragma unroll
     for (int c = 0; c < NC; ++c) fs[c] = fma(a, um[c] - up[c], fs[c]);
   }
+}
+
+template <int DIM, int LAW>
+__device__ __forceinline__ void interface_flux(const Phys& P, int two_point,
+                                               const double* __restrict__ u_f, long long own,
+                                               long long ext, int stride, const double* nf,
+                                               double* sl, double* fs) {
+  constexpr int NC = LawTraits<DIM, LAW>::NC;
+  double um[NC], up[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    um[c] = __ldcg(u_f + own + (long long)c * stride);
+    up[c] = __ldcg(u_f + ext + (long long)c * stride);
+  }
+  interface_flux_vals<DIM, LAW>(P, two_point, um, up, nf, sl, fs);
 }
 
 // ==================================================== loop B, flux-differencing form

@@ -550,15 +550,38 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 #pragma unroll
   for (int c = 0; c < 2 * NS2; ++c) si[c] = 0.0;
 
-  // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
+  // ---- phases 0/1.  All global loads of the CTA's first round are issued before any
+  // arithmetic so the DRAM round trips of the volume data (u_q, Λ_q) and of the facet data
+  // (J_f, nJf, own trace, exterior offset -> exterior trace) overlap.
+  const bool hasf = tid < nf;
+  const int fj = hasf ? tid % NF : 0, fe = hasf ? tid / NF : 0;
+  const long long fk = min(k0 + fe, G.N_e - 1);
+  const long long fgj = fk * NF + fj;
+  double fJf = 1.0, fnJ[DIM], fum[NC], fup[NC];
+  int fext = 0;
+  if (hasf) {
+    fJf = __ldcg(G.J_f + fgj);
+    fext = __ldcg(G.toff + fgj);
+#pragma unroll
+    for (int m = 0; m < DIM; ++m) fnJ[m] = __ldcg(G.nJf + fgj * DIM + m);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) fum[c] = __ldcg(u_f + fk * NC * NF + fj + (long long)c * NF);
+  }
+  double uu0[NC];
   if (active) {
     long long k = min(k0 + e, G.N_e - 1);
-    double uu[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) uu[c] = __ldcg(u_q + (k * NC + c) * NQ + i);
+    for (int c = 0; c < NC; ++c) uu0[c] = __ldcg(u_q + (k * NC + c) * NQ + i);
 #pragma unroll
     for (int c = 0; c < DD; ++c) Li[c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
-    cons_to_state<DIM, LAW>(P, uu, si);
+  }
+  if (hasf) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) fup[c] = __ldcg(u_f + fext + (long long)c * NF);
+  }
+  // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
+  if (active) {
+    cons_to_state<DIM, LAW>(P, uu0, si);
 #pragma unroll
     for (int c = 0; c < NS2; ++c) sS2[c * nq + tid] = make_double2(si[2 * c], si[2 * c + 1]);
 #pragma unroll
@@ -570,19 +593,30 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phase 1: interface numerical flux at the facet nodes
   for (int idx = tid; idx < nf; idx += 128) {
     const int j = idx % NF, ee = idx / NF;
-    long long k = min(k0 + ee, G.N_e - 1);
-    long long gj = k * NF + j;
     double nJ[DIM], nfv[DIM], sl[2 * NS2], fs[NC];
-    const double Jf = __ldcg(G.J_f + gj);
-    const int ext = __ldcg(G.toff + gj);
-#pragma unroll
-    for (int m = 0; m < DIM; ++m) nJ[m] = __ldcg(G.nJf + gj * DIM + m);
-    const double iJf = frcp(Jf);
-#pragma unroll
-    for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
 #pragma unroll
     for (int c = 0; c < 2 * NS2; ++c) sl[c] = 0.0;
-    interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
+    double Jf;
+    if (idx == tid) {            // first round: operands are already in registers
+      Jf = fJf;
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) nJ[m] = fnJ[m];
+      const double iJf = frcp(Jf);
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
+      interface_flux_vals<DIM, LAW>(P, P.two_point, fum, fup, nfv, sl, fs);
+    } else {
+      long long k = min(k0 + ee, G.N_e - 1);
+      long long gj = k * NF + j;
+      Jf = __ldcg(G.J_f + gj);
+      const int ext = __ldcg(G.toff + gj);
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) nJ[m] = __ldcg(G.nJf + gj * DIM + m);
+      const double iJf = frcp(Jf);
+#pragma unroll
+      for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
+      interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
+    }
     const double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
     for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * NF + j] = bj * fs[c];
