@@ -11,6 +11,7 @@ slow to serve as a checker: size-independent invariants of the scheme instead
 """
 import numpy as np
 import pytest
+import torch
 
 import cases
 from sse_b200.solvers import semi_discrete_residual
@@ -79,7 +80,11 @@ def test_full_size_invariants():
             A = np.einsum("qa,kq,qb->kab", V, W[None, :] / J, V)        # M_k^-1 (weight-adjusted)
             rhs = np.einsum("qp,kq,kqc->kpc", V, W[None, :] * J, w_q)   # V^T WJ w_q
             Pw = A @ rhs                                                 # projected entropy vars
-            Mdu = np.linalg.solve(A, dudt[s:e].transpose(0, 2, 1))      # M_k dudt_k
+            # M_k dudt_k: batched 35x35 solves -- checker arithmetic, done with torch on the GPU
+            # because 511 104 LAPACK calls on the host take minutes
+            At = torch.from_numpy(A).cuda()
+            Bt = torch.from_numpy(np.ascontiguousarray(dudt[s:e].transpose(0, 2, 1))).cuda()
+            Mdu = torch.linalg.solve(At, Bt).cpu().numpy()
             total += float(np.sum(Pw * Mdu))
             tscale += float(np.sum(np.abs(Pw * Mdu)))
         assert abs(total) < 1e-11 * tscale, (total, tscale)
