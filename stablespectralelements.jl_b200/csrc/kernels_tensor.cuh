@@ -483,6 +483,9 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
 #ifndef SSE_FD_KQ
 #define SSE_FD_KQ 0      // 0: two halves (ceil(KC/2) slots per part)
 #endif
+#ifndef SSE_FD_FACET_UNROLL
+#define SSE_FD_FACET_UNROLL 1
+#endif
 #ifndef SSE_FD_SINGLE_BUF
 #define SSE_FD_SINGLE_BUF 0
 #endif
@@ -703,7 +706,8 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
         // software-pipelined table reads: slot kk+1 is fetched while slot kk is evaluated
         int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node | face << 16
         double cij = __ldg(F.Cv + (half * KH) * NQ + i);
-#pragma unroll 1
+        constexpr int FACET_UNROLL = SSE_FD_FACET_UNROLL;
+#pragma unroll FACET_UNROLL
         for (int kk = half * KH; kk < kend; ++kk) {
           const int kn = (kk + 1 < kend) ? kk + 1 : kk;
           const int jp_next = __ldg(F.Cj + kn * NQ + i);
