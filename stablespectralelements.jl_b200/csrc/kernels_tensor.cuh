@@ -12,6 +12,7 @@
 //    per non-collapsed face, N1 on the collapsed one), stored in ELL format.
 #pragma once
 #include "kernels.cuh"
+#include "vmap3.cuh"
 
 namespace sse {
 
@@ -25,20 +26,24 @@ struct FastTables {
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
 
-// A[a1][b1] = sqrt(2) P_b1(eta1_a1) of the warped product (tensor_simplex.jl:84-140), one slot
-// per N1 in {3,4,5}.  With fully unrolled loops the entries become constant-bank operands of
-// the DFMAs (no load instructions) in the first-direction contractions below.
-__constant__ double c_wA[3][25];
-
 // the few table pointers the V / V^T applies need, passed BY VALUE to the out-of-line functions
-// (a reference to the kernel-parameter struct would force a local-memory copy of all of it)
+// (a reference to the kernel-parameter struct would force a local-memory copy of all of it).
+// c_wA / c_wB (constant-bank copies of the warped-product A and B tables) live in vmap3.cuh.
 struct VTab {
   const double *wA, *wB, *wC, *Vd, *VdT;
   const int* sig;
   int N_p, v_kind;
+  V3Tab v3;
 };
 __device__ __forceinline__ VTab vtab(const Tables& T) {
-  return VTab{T.wA, T.wB, T.wC, T.Vd, T.VdT, T.sig, T.N_p, T.v_kind};
+  return VTab{T.wA, T.wB, T.wC, T.Vd, T.VdT, T.sig, T.N_p, T.v_kind,
+              V3Tab{T.wC, T.wCt, T.pairtab, T.modetab}};
+}
+
+// scratch doubles the V / V^T applies need for E elements of NC components
+template <int DIM, int N1>
+__host__ __device__ constexpr int vtmp_per_column() {
+  return DIM == 3 ? V3Dims<N1>::ZS : ipow(N1, DIM);
 }
 
 // ---------------------------------------------------------------- sum-factorised V, V^T
@@ -106,67 +111,19 @@ __device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ 
     }
     __syncthreads();
   } else if constexpr (DIM == 3) {
-    constexpr int N2 = N1 * N1, N3 = N1 * N1 * N1;
-    double* Z = tmp;                 // [E][NC][b1][b2][a3]
-    double* Wt = tmp + E * NC * N3;  // [E][NC][b1][a2][a3]
-    SSE_LOOP(idx, E * N3) {
-      int a3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
-      if (b2 < N1 - b1) {
-        double acc[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-#pragma unroll
-        for (int b3 = 0; b3 < N1; ++b3)
-          if (b3 < N1 - b1 - b2) {
-            double v = __ldg(T.wC + ((a3 * N1 + b1) * N1 + b2) * N1 + b3);
-            int si = __ldg(T.sig + (b1 * N1 + b2) * N1 + b3);
-#pragma unroll
-            for (int c = 0; c < NC; ++c) acc[c] = fma(v, src[(e * NC + c) * Np + si], acc[c]);
-          }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3] = acc[c];
-      }
-    }
+    // vmap3.cuh: compact Z in tmp, stage B writes dst, stage A runs in place on dst
+    v3_stageC<N1, NC, E>(threadIdx.x, 128, T.v3, src, tmp);
     __syncthreads();
-    SSE_LOOP(idx, E * N3) {
-      int a3 = idx % N1, a2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
-      double acc[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-#pragma unroll
-      for (int b2 = 0; b2 < N1; ++b2)
-        if (b2 < N1 - b1) {
-          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            acc[c] = fma(v, Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3], acc[c]);
-        }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) Wt[(e * NC + c) * N3 + (b1 * N1 + a2) * N1 + a3] = acc[c];
-    }
+    v3_stageB<N1, E * NC>(threadIdx.x, 128, tmp, dst);
     __syncthreads();
-    // first direction: one thread per (component, a2, a3) produces all N1 outputs along a1,
-    // so every W value is loaded once and A comes from the constant bank
-    SSE_LOOP(idx, E * NC * N2) {
-      int a23 = idx % N2, ec = idx / N2;
-      double w[N1];
-#pragma unroll
-      for (int b1 = 0; b1 < N1; ++b1) w[b1] = Wt[ec * N3 + b1 * N2 + a23];
-#pragma unroll
-      for (int a1 = 0; a1 < N1; ++a1) {
-        double acc = 0.0;
-#pragma unroll
-        for (int b1 = 0; b1 < N1; ++b1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], w[b1], acc);
-        dst[ec * NQ + a1 * N2 + a23] = acc;
-      }
-    }
+    v3_stageA<N1, E * NC>(threadIdx.x, 128, dst);
     __syncthreads();
   }
 }
 
-// src [E][NC][NQ] -> dst [E][NC][N_p]
+// src [E][NC][NQ] -> dst [E][NC][N_p].  The 3-D warped product works in place on src (destroyed).
 template <int DIM, int N1, int NC, int E>
-__device__ __noinline__ void apply_Vt_t(const VTab T, const double* __restrict__ src,
+__device__ __noinline__ void apply_Vt_t(const VTab T, double* __restrict__ src,
                                            double* __restrict__ dst, double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
   const int Np = T.N_p;
@@ -229,59 +186,11 @@ __device__ __noinline__ void apply_Vt_t(const VTab T, const double* __restrict__
     }
     __syncthreads();
   } else if constexpr (DIM == 3) {
-    constexpr int N2 = N1 * N1, N3 = N1 * N1 * N1;
-    double* Wt = tmp;               // [E][NC][b1][a2][a3]
-    double* Z = tmp + E * NC * N3;  // [E][NC][b1][b2][a3]
-    SSE_LOOP(idx, E * NC * N2) {
-      int a23 = idx % N2, ec = idx / N2;
-      double x[N1];
-#pragma unroll
-      for (int a1 = 0; a1 < N1; ++a1) x[a1] = src[ec * NQ + a1 * N2 + a23];
-#pragma unroll
-      for (int b1 = 0; b1 < N1; ++b1) {
-        double acc = 0.0;
-#pragma unroll
-        for (int a1 = 0; a1 < N1; ++a1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], x[a1], acc);
-        Wt[ec * N3 + b1 * N2 + a23] = acc;
-      }
-    }
+    vt3_stageA<N1, E * NC>(threadIdx.x, 128, src);
     __syncthreads();
-    SSE_LOOP(idx, E * N3) {
-      int a3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
-      if (b2 < N1 - b1) {
-        double acc[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-#pragma unroll
-        for (int a2 = 0; a2 < N1; ++a2) {
-          double v = __ldg(T.wB + (a2 * N1 + b1) * N1 + b2);
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            acc[c] = fma(v, Wt[(e * NC + c) * N3 + (b1 * N1 + a2) * N1 + a3], acc[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3] = acc[c];
-      }
-    }
+    vt3_stageB<N1, E * NC>(threadIdx.x, 128, src, tmp);
     __syncthreads();
-    SSE_LOOP(idx, E * N3) {
-      int b3 = idx % N1, b2 = (idx / N1) % N1, b1 = (idx / N2) % N1, e = idx / N3;
-      if (b2 < N1 - b1 && b3 < N1 - b1 - b2) {
-        double acc[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-#pragma unroll
-        for (int a3 = 0; a3 < N1; ++a3) {
-          double v = __ldg(T.wC + ((a3 * N1 + b1) * N1 + b2) * N1 + b3);
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            acc[c] = fma(v, Z[(e * NC + c) * N3 + (b1 * N1 + b2) * N1 + a3], acc[c]);
-        }
-        int si = __ldg(T.sig + (b1 * N1 + b2) * N1 + b3);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) dst[(e * NC + c) * Np + si] = acc[c];
-      }
-    }
+    vt3_stageC<N1, E * NC>(threadIdx.x, 128, T.v3, tmp, dst);
     __syncthreads();
   }
 }
@@ -363,68 +272,82 @@ struct TensorNF {
                                          : 2 * DIM * ipow(N1, DIM - 1);
 };
 
-// Elements per CTA of the loop-A kernel.  NBAT > 1 batches consecutive elements as extra
-// "components" of the same thread in the V / V^T / R applies (every table entry, index
-// computation and barrier then serves NBAT*N_c FMAs).  Measured on B200 for Tet p=4 Euler:
-// NBAT = 2 is 10 % SLOWER (9.53 vs 8.65 ms / 511 k elements) because the doubled shared-memory
-// footprint halves the resident CTAs -- so it stays off for systems (it pays for scalar laws,
-// see k_standard_tensor).
+// Loop A: one CTA (128 threads) owns E = floor(128 / N_q) whole elements.  (Batching more
+// elements per CTA as extra "components" of the applies was measured 10 % slower for systems on
+// B200 -- the larger shared-memory footprint costs resident CTAs -- and is not used.)
+//
+// Shared memory (doubles):  bufQ [E*NC*NQ] | region, where the region holds the V-apply scratch
+// followed by the modal block bufP [E*NC*N_p], and is reused as bufF [E*NC*N_f] once the last
+// V / V^T apply is done.  The entropy variables overwrite the nodal values in place.  Tet p=4
+// Euler: 625 + 550 doubles = 9.4 KB per CTA, so residency is bounded by registers, not smem.
 template <int DIM, int N1>
 struct NodalCfg {
   static constexpr int NQ = ipow(N1, DIM);
   static constexpr int E = (128 / NQ) > 0 ? 128 / NQ : 1;
-  static constexpr int NBAT = 1;
-  static constexpr int ET = E * NBAT;     // elements per CTA
+  static __host__ __device__ constexpr int tmp(int NC) { return E * NC * vtmp_per_column<DIM, N1>(); }
+  static __host__ __device__ constexpr int region(int NC, int Np, int Nf) {
+    return (tmp(NC) + E * NC * Np) > E * NC * Nf ? (tmp(NC) + E * NC * Np) : E * NC * Nf;
+  }
+  static __host__ __device__ constexpr size_t bytes(int NC, int Np, int Nf) {
+    return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf));
+  }
 };
 
-// shared: bufP[ET*NC*N_p] | bufQ[ET*NC*NQ] | bufQ2[ET*NC*NQ] | bufF[ET*NC*N_f] | tmp[2*ET*NC*NQ]
+#ifndef SSE_NODAL_MINB
+#define SSE_NODAL_MINB 10
+#endif
+
 template <int DIM, int N1, int LAW, bool COLLAPSED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SSE_NODAL_MINB)
 k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
                double* __restrict__ u_f, int proj) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NQ = ipow(N1, DIM);
   using Cf = NodalCfg<DIM, N1>;
-  constexpr int E = Cf::ET;                 // elements per CTA (pointwise loops, buffers)
-  constexpr int EA = Cf::E;                 // "element" count seen by the applies ...
-  constexpr int NCA = NC * Cf::NBAT;        // ... with NBAT elements folded into the components
+  constexpr int E = Cf::E;
   constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
   extern __shared__ __align__(16) double sm[];
   const int Np = T.N_p;
-  double* bufP = sm;
-  double* bufQ = bufP + E * NC * Np;
-  double* bufQ2 = bufQ + E * NC * NQ;
-  double* bufF = bufQ2 + E * NC * NQ;
-  double* tmp = bufF + E * NC * Nf;
+  double* bufQ = sm;
+  double* tmp = bufQ + E * NC * NQ;
+  double* bufP = tmp + Cf::tmp(NC);
+  double* bufF = tmp;                      // aliases tmp/bufP; live only after the last apply
   const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
+  // own node's Jacobian for the two weightings of the projection (thread = volume node)
+  double jq = 1.0;
+  if (proj == 2 && threadIdx.x < E * NQ) {
+    const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
+    jq = __ldcg(G.J_q + min(k0 + e, G.N_e - 1) * NQ + i);
+  }
   SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? __ldcg(u + k0 * NC * Np + idx) : 1.0;
   __syncthreads();
-  apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ, tmp);
+  apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
-    apply_R_t<NQ, NCA, EA, Nf, N1>(T, bufQ, bufF);
+    apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
     SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
     return;
   }
-  SSE_LOOP(idx, E * NQ) {
-    int i = idx % NQ, e = idx / NQ;
+  if (proj != 2) {   // nodal schemes keep the nodal values themselves as u_q
+    SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
+    __syncthreads();
+  }
+  // entropy variables, in place (each thread reads and rewrites its own node only)
+  if (threadIdx.x < E * NQ) {
+    const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
     double uu[NC], w[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) uu[c] = bufQ[(e * NC + c) * NQ + i];
     cons_to_entropy<DIM, LAW>(P, uu, w);
-    double sc = 1.0;
-    if (proj == 2) {
-      long long k = min(k0 + e, G.N_e - 1);
-      sc = __ldg(T.W + i) * __ldcg(G.J_q + k * NQ + i);
-    }
+    const double sc = (proj == 2) ? __ldg(T.W + i) * jq : 1.0;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) bufQ2[(e * NC + c) * NQ + i] = w[c] * sc;
+    for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] = w[c] * sc;
   }
   __syncthreads();
   if (proj == 2) {
-    apply_Vt_t<DIM, N1, NCA, EA>(vtab(T), bufQ2, bufP, tmp);
+    apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ, bufP, tmp);
     // mass solve (weight-adjusted, M^-1 = I): V, W/J, V^T -- or the diagonal scaling
     if (T.mass_kind == MASS_DIAGONAL) {
       SSE_LOOP(idx, E * NC * NQ) {
@@ -434,23 +357,19 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
       }
       __syncthreads();
     } else {
-      apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ2, tmp);
-      SSE_LOOP(idx, E * NQ) {
-        int i = idx % NQ, e = idx / NQ;
-        long long k = min(k0 + e, G.N_e - 1);
-        double sc = fdiv(__ldg(T.W + i), __ldcg(G.J_q + k * NQ + i));
+      apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
+      if (threadIdx.x < E * NQ) {
+        const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
+        const double sc = fdiv(__ldg(T.W + i), jq);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) bufQ2[(e * NC + c) * NQ + i] *= sc;
+        for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] *= sc;
       }
       __syncthreads();
-      apply_Vt_t<DIM, N1, NCA, EA>(vtab(T), bufQ2, bufP, tmp);
+      apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ, bufP, tmp);
     }
-    apply_V_t<DIM, N1, NCA, EA>(vtab(T), bufP, bufQ2, tmp);
+    apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
   }
-  apply_R_t<NQ, NCA, EA, Nf, N1>(T, bufQ2, bufF);
-  if (proj != 2) {
-    SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
-  }
+  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
   // entropy -> conservative variables at the volume nodes (modal case) and the facet nodes,
   // one loop so the log/exp sequence is instantiated once
   const int nvol = (proj == 2) ? Ev * NQ : 0;
@@ -459,7 +378,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     const int ii = vol ? idx : idx - nvol;
     const int npt = vol ? NQ : Nf;
     const int pt = ii % npt, e = ii / npt;
-    const double* srcw = vol ? bufQ2 : bufF;
+    const double* srcw = vol ? bufQ : bufF;
     double w[NC], uu[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) w[c] = srcw[(e * NC + c) * npt + pt];
@@ -707,6 +626,10 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
         int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node | face << 16
         double cij = __ldg(F.Cv + (half * KH) * NQ + i);
         constexpr int FACET_UNROLL = SSE_FD_FACET_UNROLL;
+        int fc_prev = -1;
+        double hq[DIM];
+#pragma unroll
+        for (int n = 0; n < DIM; ++n) hq[n] = 0.0;
 #pragma unroll FACET_UNROLL
         for (int kk = half * KH; kk < kend; ++kk) {
           const int kn = (kk + 1 < kend) ? kk + 1 : kk;
@@ -721,14 +644,21 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
             sj[2 * c] = v.x;
             sj[2 * c + 1] = v.y;
           }
+          // ½ nJq of this slot's face (mesh.jl:266-271): consecutive slots of a row mostly
+          // belong to the same face (the N1 nodes of the collapsed one), so it is kept
+          if (fc != fc_prev) {
+            fc_prev = fc;
 #pragma unroll
-          for (int n = 0; n < DIM; ++n) {
-            double acc = 0.0;
+            for (int n = 0; n < DIM; ++n) {
+              double acc = 0.0;
 #pragma unroll
-            for (int m = 0; m < DIM; ++m)
-              acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
-            nJ[n] = fma(0.5, acc, sNf[n * nf + jj]);
+              for (int m = 0; m < DIM; ++m)
+                acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
+              hq[n] = 0.5 * acc;
+            }
           }
+#pragma unroll
+          for (int n = 0; n < DIM; ++n) nJ[n] = hq[n] + sNf[n * nf + jj];
           two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
           double* dst = sX + (kk - half * KH) * NC * nq + tid;
 #pragma unroll

@@ -19,6 +19,8 @@ struct Phys {
   double a[3];
   double b;
   double gamma;
+  double inv_gm1;     // 1/(gamma-1), log(gamma-1): set once on the host
+  double log_gm1;
   double half_lambda;
   int inviscid;    // sse_inviscid_flux
   int two_point;   // sse_two_point_flux used by the interface flux / volume terms
@@ -43,39 +45,47 @@ __device__ __forceinline__ double frcp(double x) {
 }
 __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b); }
 
-// logmean / inv_logmean (ConservationLaws.jl:132-156).  With q = (x-y)^2, t = (x+y)^2 the
-// reference's f^2 equals q/t and its Taylor branch (x+y)*105/(210 + f2(70 + f2(42 + 30 f2)))
-// becomes 105 (x+y) t^3 / (210 t^3 + 70 q t^2 + 42 q^2 t + 30 q^3): one division instead of
-// two.  The branch test f2 < 1e-4 is q < 1e-4 t; both branches agree to ~2e-17 relative at
-// the threshold, so a flipped decision for borderline arguments is harmless.
-__device__ __forceinline__ void logmean_terms(double x, double y, double& num, double& den,
-                                              bool& taylor) {
-  double d = x - y, s = x + y;
-  double q = d * d, t = s * s;
-  taylor = q < 1.0e-4 * t;
-  double q2 = q * q;
-  den = fma(t, fma(t, fma(210.0, t, 70.0 * q), 42.0 * q2), 30.0 * q * q2);
-  num = 105.0 * s * t * t * t;
+// reciprocal good to ~2^-44 relative (seed + one Newton step): enough wherever the result only
+// enters through f^2 < 1e-4 (see logmean below)
+__device__ __forceinline__ double frcp1(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  return fma(y, e, y);
 }
 
+// logmean / inv_logmean (ConservationLaws.jl:132-156).  The reference's
+//   f^2 = (x(x-2y)+y^2)/(x(x+2y)+y^2) = ((x-y)/(x+y))^2,
+// and on its Taylor branch (f^2 < 1e-4), with z = f^2/3 + f^4/5 + f^6/7,
+//   logmean     = (x+y) 105/(210 + f^2(70 + f^2(42 + 30 f^2))) = (x+y)/2 / (1 + z)
+//   inv_logmean = 2/(x+y) (1 + z)                                  (a finite polynomial).
+// 1/(1+z) is expanded as 1 - f^2/3 - 4/45 f^4 - 44/945 f^6 (+0.081 f^8 < 1e-17, dropped), so
+// logmean needs no full-precision division: 1/(x+y) only enters through f^2, whose relative
+// error e contributes e*f^2/3 < 4e-5 e to the result -- one Newton step (e ~ 6e-14) is ample.
+// inv_logmean needs 1/(x+y) itself and reuses it for f.  Both agree with the reference's
+// formula to ~2 ulp; a flipped branch decision at the threshold is harmless (the branches
+// agree to ~2e-17 relative there).
 // rare branch (|x-y|/(x+y) >= 1e-2): kept out of line so the common path stays small
 __device__ __noinline__ double logmean_full(double x, double y) { return (y - x) / log(y / x); }
 
 __device__ __forceinline__ double logmean(double x, double y) {
-  double num, den;
-  bool taylor;
-  logmean_terms(x, y, num, den, taylor);
-  double r = fdiv(num, den);
-  if (!taylor) r = logmean_full(x, y);
+  const double d = x - y, s = x + y;
+  const double g = d * frcp1(s);
+  const double f2 = g * g;
+  const double pl = fma(f2, fma(f2, fma(f2, -44.0 / 945.0, -4.0 / 45.0), -1.0 / 3.0), 1.0);
+  double r = (0.5 * s) * pl;
+  if (!(f2 < 1.0e-4)) r = logmean_full(x, y);
   return r;
 }
 
 __device__ __forceinline__ double inv_logmean(double x, double y) {
-  double num, den;
-  bool taylor;
-  logmean_terms(x, y, num, den, taylor);
-  double r = fdiv(den, num);
-  if (!taylor) r = frcp(logmean_full(x, y));
+  const double d = x - y, s = x + y;
+  const double is = frcp(s);
+  const double g = d * is;
+  const double f2 = g * g;
+  const double pl = fma(f2, fma(f2, fma(f2, 1.0 / 7.0, 1.0 / 5.0), 1.0 / 3.0), 1.0);
+  double r = (is + is) * pl;
+  if (!(f2 < 1.0e-4)) r = frcp(logmean_full(x, y));
   return r;
 }
 
@@ -110,7 +120,7 @@ __device__ __forceinline__ void state_to_cons(const Phys& P, const double* s, do
       u[1 + m] = s[0] * s[1 + m];
       k += s[1 + m] * s[1 + m];
     }
-    u[DIM + 1] = s[DIM + 1] / (P.gamma - 1.0) + 0.5 * s[0] * k;
+    u[DIM + 1] = s[DIM + 1] * P.inv_gm1 + 0.5 * s[0] * k;
   } else {
     u[0] = s[0];
   }
@@ -128,7 +138,7 @@ __device__ __forceinline__ void physical_flux_c(const Phys& P, const double* s, 
       k += s[1 + m] * s[1 + m];
     }
     double rho = s[0], p = s[DIM + 1];
-    double E = p / (P.gamma - 1.0) + 0.5 * rho * k;
+    double E = p * P.inv_gm1 + 0.5 * rho * k;
     out[0] = rho * vc;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) out[1 + m] = rho * s[1 + m] * vc + p * c[m];
@@ -160,7 +170,7 @@ __device__ __forceinline__ void two_point_flux_c(const Phys& P, int kind, const 
         vlc += L[1 + m] * c[m];
         vrc += R[1 + m] * c[m];
       }
-      double C = 0.5 * vlvr + inv_logmean(L[DIM + 2], R[DIM + 2]) / (P.gamma - 1.0);
+      double C = 0.5 * vlvr + inv_logmean(L[DIM + 2], R[DIM + 2]) * P.inv_gm1;
       double f_rho = rho_avg * vc;
       out[0] = f_rho;
 #pragma unroll
@@ -218,11 +228,11 @@ __device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, 
     double k = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) k += u[1 + m] * u[1 + m];
-    k *= 0.5 / u[0];
+    k *= 0.5 * frcp(u[0]);
     double p = gm1 * (u[DIM + 1] - k);
     double inv_p = frcp(p);
     // log(p / rho^gamma) = log p - gamma log rho (two logs instead of pow + log)
-    w[0] = (g - (log(p) - g * log(u[0]))) / gm1 - k * inv_p;
+    w[0] = (g - (log(p) - g * log(u[0]))) * P.inv_gm1 - k * inv_p;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) w[1 + m] = u[1 + m] * inv_p;
     w[DIM + 1] = -u[0] * inv_p;
@@ -234,7 +244,7 @@ __device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, 
 template <int DIM, int LAW>
 __device__ __forceinline__ void entropy_to_cons(const Phys& P, const double* w_in, double* u) {
   if constexpr (LAW == LAW_EULER) {
-    double g = P.gamma, gm1 = g - 1.0, inv_gm1 = 1.0 / gm1;
+    double g = P.gamma, gm1 = g - 1.0, inv_gm1 = P.inv_gm1;
     double w[DIM + 2];
 #pragma unroll
     for (int e = 0; e < DIM + 2; ++e) w[e] = w_in[e] * gm1;
@@ -244,7 +254,7 @@ __device__ __forceinline__ void entropy_to_cons(const Phys& P, const double* w_i
     k = fdiv(k, 2.0 * w[DIM + 1]);
     double s = g - w[0] + k;
     // ((gm1 / (-w_last)^g)^(1/gm1)) exp(-s/gm1) = exp((log gm1 - g log(-w_last) - s) / gm1)
-    double rho_e = exp((log(gm1) - g * log(-w[DIM + 1]) - s) * inv_gm1);
+    double rho_e = exp((P.log_gm1 - g * log(-w[DIM + 1]) - s) * inv_gm1);
     u[0] = -w[DIM + 1] * rho_e;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) u[1 + m] = w[1 + m] * rho_e;

@@ -205,13 +205,10 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
 
 template <int DIM, int N1, int LAW>
 static int launch_a_fast(sse_handle* h, const double* u_dev) {
-  constexpr int NQ = ipow(N1, DIM);
-  constexpr int EL = NodalCfg<DIM, N1>::ET;
+  constexpr int EL = NodalCfg<DIM, N1>::E;
   if (TensorNF<DIM, N1, true>::value != h->cfg.N_f)
     return fail("facet-node count does not match the specialised kernel");
-  const int Nc = h->cfg.N_c;
-  const size_t smem = sizeof(double) * (size_t)EL *
-                      ((size_t)Nc * h->cfg.N_p + 4 * (size_t)Nc * NQ + (size_t)Nc * h->cfg.N_f);
+  const size_t smem = NodalCfg<DIM, N1>::bytes(h->cfg.N_c, h->cfg.N_p, h->cfg.N_f);
   CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
@@ -401,19 +398,35 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     if (d == 3 && dev_upload(h, ops->warp_C, (size_t)n * n * n * n, &pC)) return -1;
     if (dev_upload(h, ops->sigma_i, nd, &ps)) return -1;
     T.wA = pA; T.wB = pB; T.wC = pC; T.sig = ps;
+    if (d == 3) {
+      // derived tables of the specialised 3-D applies (vmap3.cuh)
+      V3HostTables ht;
+      if (v3_build_tables(n, ops->sigma_i, ops->warp_C, ht)) {
+        if (dev_upload_vec(h, ht.wCt, &T.wCt) || dev_upload_vec(h, ht.pairtab, &T.pairtab) ||
+            dev_upload_vec(h, ht.modetab, &T.modetab))
+          return -1;
+      } else {
+        h->const_conflict = 1;   // modes not ordered b3-fastest: generic kernels only
+      }
+    }
     if (n >= 3 && n <= 5) {
       // constant-bank copy of A for the specialised kernels (one slot per n); two handles with
       // different A tables for the same n cannot share it
-      static double seen[3][25];
+      static double seen[3][25], seenB[3][125];
       static bool have[3] = {false, false, false};
       bool same = true;
       for (int q = 0; q < n * n; ++q) same = same && (!have[n - 3] || seen[n - 3][q] == ops->warp_A[q]);
+      for (int q = 0; q < n * n * n; ++q)
+        same = same && (!have[n - 3] || seenB[n - 3][q] == ops->warp_B[q]);
       if (!same) h->const_conflict = 1;
       else {
         for (int q = 0; q < n * n; ++q) seen[n - 3][q] = ops->warp_A[q];
+        for (int q = 0; q < n * n * n; ++q) seenB[n - 3][q] = ops->warp_B[q];
         have[n - 3] = true;
         CU(cudaMemcpyToSymbol(c_wA, ops->warp_A, sizeof(double) * n * n,
                               sizeof(double) * 25 * (n - 3)));
+        CU(cudaMemcpyToSymbol(c_wB, ops->warp_B, sizeof(double) * n * n * n,
+                              sizeof(double) * 125 * (n - 3)));
       }
     }
   } else if (cfg->v_kind == SSE_V_IDENTITY) {
@@ -669,6 +682,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   Phys& P = h->P;
   for (int m = 0; m < 3; ++m) P.a[m] = cfg->a[m];
   P.b = cfg->b; P.gamma = cfg->gamma; P.half_lambda = cfg->half_lambda;
+  P.inv_gm1 = 1.0 / (cfg->gamma - 1.0); P.log_gm1 = std::log(cfg->gamma - 1.0);
   P.inviscid = cfg->inviscid_flux;
   P.two_point = (cfg->form == SSE_FORM_FLUX_DIFFERENCING) ? cfg->two_point_flux : 0;
 
@@ -754,8 +768,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_std = 0;
   }
   auto smem_a_fast = [&](int E) {
-    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf +
-                                         2 * (size_t)Nc * Nq);
+    // upper bound of NodalCfg::bytes (the launch computes the exact figure)
+    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf);
   };
   auto smem_b_fast = [&](int E) {
     const size_t H = (size_t)h->n1 / 2;

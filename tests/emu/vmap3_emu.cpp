@@ -1,0 +1,37 @@
+// Host emulation of the device stage functions in csrc/vmap3.cuh: every stage is run as a loop
+// over the thread index with the same barriers the kernels place between stages.  Test
+// infrastructure only (tests/test_vmap3_host.py); validates the index logic without a GPU.
+#define SSE_HOST_EMU 1
+#include <cmath>
+#include <cstring>
+#include "../../stablespectralelements.jl_b200/csrc/vmap3.cuh"
+
+using namespace sse;
+
+template <int N1, int NC, int E>
+static void run(int transpose, V3Tab T, double* src, double* dst, double* Z, int nthr) {
+  constexpr int EC = E * NC;
+  if (!transpose) {
+    for (int t = 0; t < nthr; ++t) v3_stageC<N1, NC, E>(t, nthr, T, src, Z);
+    for (int t = 0; t < nthr; ++t) v3_stageB<N1, EC>(t, nthr, Z, dst);
+    for (int t = 0; t < nthr; ++t) v3_stageA<N1, EC>(t, nthr, dst);
+  } else {
+    for (int t = 0; t < nthr; ++t) vt3_stageA<N1, EC>(t, nthr, src);
+    for (int t = 0; t < nthr; ++t) vt3_stageB<N1, EC>(t, nthr, src, Z);
+    for (int t = 0; t < nthr; ++t) vt3_stageC<N1, EC>(t, nthr, T, Z, dst);
+  }
+}
+
+extern "C" int vmap3_emu(int n1, int nc, int e, int transpose, const double* wA, const double* wB,
+                         const double* wC, const int* sigma, double* src, double* dst, double* Z,
+                         int nthr) {
+  std::memcpy(c_wA[n1 - 3], wA, sizeof(double) * n1 * n1);
+  std::memcpy(c_wB[n1 - 3], wB, sizeof(double) * n1 * n1 * n1);
+  V3HostTables ht;
+  if (!v3_build_tables(n1, sigma, wC, ht)) return -2;
+  V3Tab T{wC, ht.wCt.data(), ht.pairtab.data(), ht.modetab.data()};
+#define CASE(N, C, EE) if (n1 == N && nc == C && e == EE) { run<N, C, EE>(transpose, T, src, dst, Z, nthr); return 0; }
+  CASE(5, 5, 1) CASE(5, 1, 1) CASE(5, 4, 1) CASE(4, 5, 2) CASE(4, 1, 2) CASE(3, 5, 4) CASE(3, 1, 4)
+  CASE(4, 4, 1) CASE(3, 4, 1)
+  return -1;
+}
