@@ -22,6 +22,15 @@ struct FastTables {
   const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
   const double* Rv;    // [KC][NQ] R[j, i]
   const double* D1;    // [DIM][N1][N1] 1-D derivative matrices of D_eta (row-major)
+  // work list of the facet-correction column sums, one run per exchanged part: entry =
+  // facet node | comp << 16 (comp 15 = all components), -1 = idle lane; runs are padded so that
+  // the long (collapsed-face) sums fill whole warps.  red_off[p]..red_off[p+1] delimit part p.
+  const int* red;
+  int red_off[5];
+  // by value (constant bank, uniform indexing): face of ELL slot k (the same for every row) and
+  // the reference normals [face][DIM]
+  int slot_face[12];
+  double nref[12];
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
@@ -623,7 +632,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
       if (active) {
         const int kend = (half + 1) * KH < KC ? (half + 1) * KH : KC;
         // software-pipelined table reads: slot kk+1 is fetched while slot kk is evaluated
-        int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node | face << 16
+        int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node (| face << 16, unused)
         double cij = __ldg(F.Cv + (half * KH) * NQ + i);
         constexpr int FACET_UNROLL = SSE_FD_FACET_UNROLL;
         int fc_prev = -1;
@@ -635,7 +644,8 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
           const int kn = (kk + 1 < kend) ? kk + 1 : kk;
           const int jp_next = __ldg(F.Cj + kn * NQ + i);
           const double cij_next = __ldg(F.Cv + kn * NQ + i);
-          const int j = jp & 0xffff, fc = jp >> 16;
+          const int j = jp & 0xffff;
+          const int fc = F.slot_face[kk];     // uniform: slot k lies on the same face in every row
           const int jj = e * NF + j;
           double nJ[DIM], sj[2 * NS2], f[NC];
 #pragma unroll
@@ -644,16 +654,15 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
             sj[2 * c] = v.x;
             sj[2 * c + 1] = v.y;
           }
-          // ½ nJq of this slot's face (mesh.jl:266-271): consecutive slots of a row mostly
-          // belong to the same face (the N1 nodes of the collapsed one), so it is kept
+          // ½ nJq of this slot's face (mesh.jl:266-271): consecutive slots mostly belong to the
+          // same face (the N1 nodes of the collapsed one), so it is kept across slots
           if (fc != fc_prev) {
             fc_prev = fc;
 #pragma unroll
             for (int n = 0; n < DIM; ++n) {
               double acc = 0.0;
 #pragma unroll
-              for (int m = 0; m < DIM; ++m)
-                acc = fma(Li[m + DIM * n], __ldg(T.n_ref + fc * DIM + m), acc);
+              for (int m = 0; m < DIM; ++m) acc = fma(Li[m + DIM * n], F.nref[fc * DIM + m], acc);
               hq[n] = 0.5 * acc;
             }
           }
@@ -672,27 +681,50 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
         }
       }
       __syncthreads();
-      // f_f -= column sums of this half's terms: the terms of facet node j sit in ELL slot k
-      // at an arithmetic progression of volume nodes (R_desc), no index loads
-      for (int idx = tid; idx < NC * nf; idx += 128) {
-        const int c = idx % NC, ej = idx / NC;
-        const int j = ej % NF, ee = ej / NF;
+      // f_f -= column sums of this part's terms: the terms of facet node j sit in ELL slot k at
+      // an arithmetic progression of volume nodes (R_desc).  The host-built work list gives
+      // every lane either one facet node with all components (N1-term sums) or one
+      // (node, component) pair of the collapsed face (N1^2-term sums), whole warps of each kind.
+      for (int t = F.red_off[half] + tid; t < F.red_off[half + 1]; t += 128) {
+        const int ent = __ldg(F.red + t);
+        if (ent < 0) continue;
+        const int j = ent & 0xffff, cm = ent >> 16;
         const int desc = __ldg(T.R_desc + j);
         const int kslot = (desc >> 27) & 31;
-        if (kslot / KH == half) {
-          const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
-          const double* base = sX + ((kslot - half * KH) * NC + c) * nq + ee * NQ + start;
-          double acc = 0.0;
-          if (cnt == N1) {                       // one tensor line
+        const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
 #pragma unroll
-            for (int q = 0; q < N1; ++q) acc += base[q * stride];
-          } else if (cnt == N1 * N1 && stride == 1) {   // block behind a collapsed-face node
+        for (int ee = 0; ee < EL; ++ee) {
+          const double* base = sX + (kslot - half * KH) * NC * nq + ee * NQ + start;
+          double* ff = sFf + ee * NC * NF + j;
+          if (cm == 15) {
 #pragma unroll
-            for (int q = 0; q < N1 * N1; ++q) acc += base[q];
+            for (int c = 0; c < NC; ++c) {
+              const double* bc = base + c * nq;
+              double acc = 0.0;
+              if (cnt == N1) {                       // one tensor line
+#pragma unroll
+                for (int q = 0; q < N1; ++q) acc += bc[q * stride];
+              } else {
+                for (int q = 0; q < cnt; ++q) acc += bc[q * stride];
+              }
+              ff[c * NF] -= acc;
+            }
           } else {
-            for (int q = 0; q < cnt; ++q) acc += base[q * stride];
+            const double* bc = base + cm * nq;
+            double acc = 0.0;
+            if (cnt == N1 * N1 && stride == 1) {     // block behind a collapsed-face node
+              double part[N1];
+#pragma unroll
+              for (int q2 = 0; q2 < N1; ++q2) part[q2] = bc[q2];
+#pragma unroll
+              for (int q = N1; q < N1 * N1; ++q) part[q % N1] += bc[q];
+#pragma unroll
+              for (int q2 = 0; q2 < N1; ++q2) acc += part[q2];
+            } else {
+              for (int q = 0; q < cnt; ++q) acc += bc[q * stride];
+            }
+            ff[cm * NF] -= acc;
           }
-          sFf[(ee * NC + c) * NF + j] -= acc;
         }
       }
     }

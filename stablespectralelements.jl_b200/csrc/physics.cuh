@@ -65,28 +65,51 @@ __device__ __forceinline__ double frcp1(double x) {
 // inv_logmean needs 1/(x+y) itself and reuses it for f.  Both agree with the reference's
 // formula to ~2 ulp; a flipped branch decision at the threshold is harmless (the branches
 // agree to ~2e-17 relative there).
+// The polynomial coefficients and the threshold live in constant memory: sm_100 FP64
+// instructions take no 64-bit immediates, so a literal costs two UMOVs per use where a
+// constant-bank value costs one LDCU.
+__constant__ double c_lm[8] = {-1.0 / 3.0, -4.0 / 45.0, -44.0 / 945.0,   // 1/(1+z) series
+                               1.0 / 3.0,  1.0 / 5.0,   1.0 / 7.0,       // 1 + z
+                               1.0e-4, 0.0};
+
 // rare branch (|x-y|/(x+y) >= 1e-2): kept out of line so the common path stays small
 __device__ __noinline__ double logmean_full(double x, double y) { return (y - x) / log(y / x); }
 
-__device__ __forceinline__ double logmean(double x, double y) {
+// Taylor-branch values; f2 is returned so that callers can test both means with one branch
+__device__ __forceinline__ double logmean_taylor(double x, double y, double& f2) {
   const double d = x - y, s = x + y;
   const double g = d * frcp1(s);
-  const double f2 = g * g;
-  const double pl = fma(f2, fma(f2, fma(f2, -44.0 / 945.0, -4.0 / 45.0), -1.0 / 3.0), 1.0);
-  double r = (0.5 * s) * pl;
-  if (!(f2 < 1.0e-4)) r = logmean_full(x, y);
+  f2 = g * g;
+  const double pl = fma(fma(fma(f2, c_lm[2], c_lm[1]), f2, c_lm[0]), f2, 1.0);
+  return (0.5 * s) * pl;
+}
+__device__ __forceinline__ double inv_logmean_taylor(double x, double y, double& f2) {
+  const double d = x - y, s = x + y;
+  const double is = frcp(s);
+  const double g = d * is;
+  f2 = g * g;
+  const double pl = fma(fma(fma(f2, c_lm[5], c_lm[4]), f2, c_lm[3]), f2, 1.0);
+  return (is + is) * pl;
+}
+
+__device__ __forceinline__ double logmean(double x, double y) {
+  double f2;
+  double r = logmean_taylor(x, y, f2);
+  if (!(f2 < c_lm[6])) r = logmean_full(x, y);
   return r;
 }
 
 __device__ __forceinline__ double inv_logmean(double x, double y) {
-  const double d = x - y, s = x + y;
-  const double is = frcp(s);
-  const double g = d * is;
-  const double f2 = g * g;
-  const double pl = fma(f2, fma(f2, fma(f2, 1.0 / 7.0, 1.0 / 5.0), 1.0 / 3.0), 1.0);
-  double r = (is + is) * pl;
-  if (!(f2 < 1.0e-4)) r = frcp(logmean_full(x, y));
+  double f2;
+  double r = inv_logmean_taylor(x, y, f2);
+  if (!(f2 < c_lm[6])) r = frcp(logmean_full(x, y));
   return r;
+}
+
+// both means of the Ranocha flux when at least one of them left the Taylor branch (rare):
+// .x = logmean(x0, y0), .y = inv_logmean(x1, y1)
+__device__ __noinline__ double2 logmeans_slow(double x0, double y0, double x1, double y1) {
+  return make_double2(logmean(x0, y0), inv_logmean(x1, y1));
 }
 
 // conservative -> shared-memory state
@@ -158,7 +181,14 @@ __device__ __forceinline__ void two_point_flux_c(const Phys& P, int kind, const 
                                                  const double* R, const double* c, double* out) {
   if constexpr (LAW == LAW_EULER) {
     if (kind == 1) {  // entropy-conservative (Ranocha), euler_navierstokes.jl:171-195
-      double rho_avg = logmean(L[0], R[0]);
+      double f2a, f2b;
+      double rho_avg = logmean_taylor(L[0], R[0], f2a);
+      double ilm = inv_logmean_taylor(L[DIM + 2], R[DIM + 2], f2b);
+      if (!((f2a < c_lm[6]) && (f2b < c_lm[6]))) {   // one (rare) branch for both means
+        const double2 m = logmeans_slow(L[0], R[0], L[DIM + 2], R[DIM + 2]);
+        rho_avg = m.x;
+        ilm = m.y;
+      }
       double p_avg = 0.5 * (L[DIM + 1] + R[DIM + 1]);
       double vlvr = 0.0, vc = 0.0, vlc = 0.0, vrc = 0.0;
       double vavg[DIM];
@@ -170,7 +200,7 @@ __device__ __forceinline__ void two_point_flux_c(const Phys& P, int kind, const 
         vlc += L[1 + m] * c[m];
         vrc += R[1 + m] * c[m];
       }
-      double C = 0.5 * vlvr + inv_logmean(L[DIM + 2], R[DIM + 2]) * P.inv_gm1;
+      double C = fma(ilm, P.inv_gm1, 0.5 * vlvr);
       double f_rho = rho_avg * vc;
       out[0] = f_rho;
 #pragma unroll

@@ -586,6 +586,40 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
         if (dev_upload_vec(h, Cj, &h->F.Cj) || dev_upload_vec(h, Cvv, &h->F.Cv) ||
             dev_upload_vec(h, Rvv, &h->F.Rv) || dev_upload_vec(h, D1, &h->F.D1))
           return -1;
+        // face of every ELL slot (must not depend on the row) and the reference normals, by value
+        bool slots_ok = kc <= 12 && cfg->num_faces * d <= 12 && ops->n_ref != nullptr;
+        for (int q = 0; q < kc && slots_ok; ++q) {
+          const int f0 = Rt.ci[Rt.rp[0] + q] / T.npf;
+          for (int i = 0; i < Nq; ++i) slots_ok = slots_ok && (Rt.ci[Rt.rp[i] + q] / T.npf == f0);
+          h->F.slot_face[q] = f0;
+        }
+        if (slots_ok)
+          for (int q = 0; q < cfg->num_faces * d; ++q) h->F.nref[q] = ops->n_ref[q];
+        // work list of the facet-correction column sums (kernels_tensor.cuh, FastTables::red)
+        {
+          const int KHh = SSE_FD_KQ > 0 ? SSE_FD_KQ : (kc + 1) / 2;
+          const int nparts = (kc + KHh - 1) / KHh;
+          std::vector<int> red;
+          slots_ok = slots_ok && nparts <= 4;
+          for (int part = 0; part < nparts && slots_ok; ++part) {
+            h->F.red_off[part] = (int)red.size();
+            std::vector<int> lines, blocks;
+            for (int j = 0; j < Nf; ++j) {
+              const int b = R.rp[j], cnt = R.rp[j + 1] - b;
+              const int k = Rslot[b] - Rt.rp[R.ci[b]];
+              if (k / KHh != part) continue;
+              (cnt > n1 ? blocks : lines).push_back(j);
+            }
+            for (int j : blocks)
+              for (int c = 0; c < Nc; ++c) red.push_back(j | (c << 16));
+            while (red.size() % 32) red.push_back(-1);
+            for (int j : lines) red.push_back(j | (15 << 16));
+            while (red.size() % 32) red.push_back(-1);
+          }
+          for (int part = nparts; part <= 4; ++part) h->F.red_off[part] = (int)red.size();
+          if (dev_upload_vec(h, red, &h->F.red)) return -1;
+        }
+        ok = ok && (slots_ok || cfg->form != SSE_FORM_FLUX_DIFFERENCING);
         h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
         h->fast_std = (cfg->form == SSE_FORM_STANDARD) ? 1 : 0;
       }

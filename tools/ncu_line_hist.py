@@ -8,7 +8,7 @@ hdr = None; cur = None; fname = ""
 agg = collections.defaultdict(lambda: [0, 0, ""])
 tot = stot = 0
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name": fname = r[1].split("/")[-1]; continue
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"): fname = r[1].split("/")[-1]; continue
     if hdr is None:
         if "Instructions Executed" in r: hdr = r; iN = r.index("Instructions Executed"); iS = r.index("# Samples")
         continue
