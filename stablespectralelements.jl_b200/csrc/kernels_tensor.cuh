@@ -57,7 +57,7 @@ __host__ __device__ constexpr int vtmp_per_column() {
 
 // ---------------------------------------------------------------- sum-factorised V, V^T
 // src [E][NC][N_p] -> dst [E][NC][NQ]; every thread carries all NC components of one output.
-template <int DIM, int N1, int NC, int E>
+template <int DIM, int N1, int NC, int E, bool OOL = false>
 __device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ src,
                                           double* __restrict__ dst, double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
@@ -123,7 +123,7 @@ __device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ 
     // vmap3.cuh: compact Z in tmp, stage B writes dst, stage A runs in place on dst
     v3_stageC<N1, NC, E>(threadIdx.x, 128, T.v3, src, tmp);
     __syncthreads();
-    v3_stageB<N1, E * NC>(threadIdx.x, 128, tmp, dst);
+    v3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, tmp, dst);
     __syncthreads();
     v3_stageA<N1, E * NC>(threadIdx.x, 128, dst);
     __syncthreads();
@@ -131,7 +131,7 @@ __device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ 
 }
 
 // src [E][NC][NQ] -> dst [E][NC][N_p].  The 3-D warped product works in place on src (destroyed).
-template <int DIM, int N1, int NC, int E>
+template <int DIM, int N1, int NC, int E, bool OOL = false>
 __device__ __noinline__ void apply_Vt_t(const VTab T, double* __restrict__ src,
                                            double* __restrict__ dst, double* __restrict__ tmp) {
   constexpr int NQ = ipow(N1, DIM);
@@ -197,7 +197,7 @@ __device__ __noinline__ void apply_Vt_t(const VTab T, double* __restrict__ src,
   } else if constexpr (DIM == 3) {
     vt3_stageA<N1, E * NC>(threadIdx.x, 128, src);
     __syncthreads();
-    vt3_stageB<N1, E * NC>(threadIdx.x, 128, src, tmp);
+    vt3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, src, tmp);
     __syncthreads();
     vt3_stageC<N1, E * NC>(threadIdx.x, 128, T.v3, tmp, dst);
     __syncthreads();
@@ -332,7 +332,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   }
   SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? __ldcg(u + k0 * NC * Np + idx) : 1.0;
   __syncthreads();
-  apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
+  apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
     apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
@@ -356,7 +356,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   }
   __syncthreads();
   if (proj == 2) {
-    apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ, bufP, tmp);
+    apply_Vt_t<DIM, N1, NC, E, true>(vtab(T), bufQ, bufP, tmp);
     // mass solve (weight-adjusted, M^-1 = I): V, W/J, V^T -- or the diagonal scaling
     if (T.mass_kind == MASS_DIAGONAL) {
       SSE_LOOP(idx, E * NC * NQ) {
@@ -366,7 +366,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
       }
       __syncthreads();
     } else {
-      apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
+      apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
       if (threadIdx.x < E * NQ) {
         const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
         const double sc = fdiv(__ldg(T.W + i), jq);
@@ -374,9 +374,9 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
         for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] *= sc;
       }
       __syncthreads();
-      apply_Vt_t<DIM, N1, NC, E>(vtab(T), bufQ, bufP, tmp);
+      apply_Vt_t<DIM, N1, NC, E, true>(vtab(T), bufQ, bufP, tmp);
     }
-    apply_V_t<DIM, N1, NC, E>(vtab(T), bufP, bufQ, tmp);
+    apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   }
   apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
   // entropy -> conservative variables at the volume nodes (modal case) and the facet nodes,
