@@ -174,6 +174,26 @@ int sse_measure_fp64_peak(int device, double* tflops);
 int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
 int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
 
+/* ---- analysis functionals on the device --------------------------------------
+ * Analysis/conservation.jl:113-190 (evaluate_conservation, evaluate_conservation_residual for the
+ * PrimaryConservation / EnergyConservation / EntropyConservation analyses) and
+ * Analysis/error.jl:58-91 (L2 error, default error quadrature = volume quadrature), evaluated on
+ * the handle's device-resident state u and last residual dudt.  Sums run in a fixed order.
+ *   SSE_FN_CONSERVATION      out[e] = sum_k 1^T W J_k V x_k[:,e]; x = u or dudt (arg)   N_c values
+ *   SSE_FN_ENTROPY           out[0] = sum_k sum_i W_i J_ki S((V u_k)_i)                 1 value
+ *   SSE_FN_ENERGY            out[e] = 1/2 sum_k u_k^T M_k u_k                           N_c values
+ *   SSE_FN_ENERGY_RESIDUAL   out[e] = sum_k u_k^T M_k dudt_k                            N_c values
+ *   SSE_FN_ENTROPY_RESIDUAL  out[0] = sum_k (P_k w(V u_k))^T M_k dudt_k                 1 value
+ *   SSE_FN_L2_ERROR          out[e] = sqrt(sum_k sum_i W_i J_ki (exact - V u)^2);       N_c values
+ *                            exact_q_host = exact solution at the volume nodes, (N_q, N_c, N_e)
+ * M_k is the mass matrix of the handle's mass solver (mass_matrix.jl:138-151).                */
+enum sse_functional_kind {
+  SSE_FN_CONSERVATION = 0, SSE_FN_ENTROPY = 1, SSE_FN_ENERGY = 2, SSE_FN_ENERGY_RESIDUAL = 3,
+  SSE_FN_ENTROPY_RESIDUAL = 4, SSE_FN_L2_ERROR = 5
+};
+enum sse_functional_arg { SSE_ARG_STATE = 0, SSE_ARG_DUDT = 1 };
+int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 #include "../../include/sse_b200.h"
 #include "kernels.cuh"
 #include "kernels_tensor.cuh"
+#include "functionals.cuh"
 
 using namespace sse;
 
@@ -300,6 +301,31 @@ static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
 }
 
 // ------------------------------------------------------------------------------- API
+// ---- analysis functionals (functionals.cuh)
+template <int DIM, int LAW>
+static int launch_functional(sse_handle* h, int which, const double* xa, const double* xb,
+                             double* partial, int n_out) {
+  const int Nc = h->cfg.N_c, Np = h->cfg.N_p, Nq = h->cfg.N_q;
+  size_t wt = 1;
+  for (int m = 0; m < DIM; ++m) wt *= (size_t)std::max(h->T.n1, 1);
+  const size_t smem = sizeof(double) * ((size_t)Nc * (6 * (size_t)Np + 2 * (size_t)Nq + 2 * wt) + 32);
+  if (smem > 200 * 1024) return fail("element too large for the functional kernel (%zu B)", smem);
+  CU(cudaFuncSetAttribute(k_functional<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  Geo G = h->G;
+  G.k_begin = 0;
+  k_functional<DIM, LAW><<<(unsigned)h->cfg.N_e, 128, smem, h->stream>>>(h->T, G, h->P, which, xa,
+                                                                         xb, partial, n_out);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+static int run_functional(sse_handle* h, int which, const double* xa, const double* xb,
+                          double* partial, int n_out) {
+  SSE_DISPATCH(launch_functional, h, which, xa, xb, partial, n_out);
+}
+
+
 extern "C" {
 
 const char* sse_last_error(void) { return g_err.c_str(); }
@@ -1101,6 +1127,51 @@ int sse_sync(sse_handle* h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host, double* out) {
+  if (!h || !out) return fail("null argument");
+  if (which < SSE_FN_CONSERVATION || which > SSE_FN_L2_ERROR) return fail("unknown functional %d", which);
+  CU(cudaSetDevice(h->cfg.device));
+  const int Nc = h->cfg.N_c, Nq = h->cfg.N_q;
+  const int64_t Ne = h->cfg.N_e;
+  const int n_out = (which == SSE_FN_ENTROPY || which == SSE_FN_ENTROPY_RESIDUAL) ? 1 : Nc;
+  const double* xa = h->u;
+  const double* xb = h->dudt;
+  if (which == SSE_FN_CONSERVATION && arg == SSE_ARG_DUDT) xa = h->dudt;
+  double* exact_dev = nullptr;
+  if (which == SSE_FN_L2_ERROR) {
+    if (!exact_q_host) return fail("the L2 error needs the exact solution at the volume nodes");
+    const size_t n = (size_t)Nq * Nc * Ne;
+    CU(cudaMalloc(&exact_dev, n * sizeof(double)));
+    CU(cudaMemcpyAsync(exact_dev, exact_q_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    xb = exact_dev;
+  }
+  const int nblk = (int)std::min<int64_t>(256, Ne);
+  const int64_t chunk = (Ne + nblk - 1) / nblk;
+  double *partial = nullptr, *blocks = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&partial, (size_t)Ne * n_out * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&blocks, (size_t)nblk * n_out * sizeof(double)) != cudaSuccess)
+    rc = fail("out of device memory for the functional partial sums");
+  std::vector<double> hb((size_t)nblk * n_out);
+  if (!rc) rc = run_functional(h, which, xa, xb, partial, n_out);
+  if (!rc) {
+    k_reduce_partials<<<nblk, 256, 0, h->stream>>>(partial, Ne, n_out, chunk, blocks);
+    h->launches++;
+    if (cudaMemcpyAsync(hb.data(), blocks, hb.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                        h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+      rc = fail("functional: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaFree(partial); cudaFree(blocks); cudaFree(exact_dev);
+  if (rc) return rc;
+  for (int c = 0; c < n_out; ++c) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += hb[(size_t)b * n_out + c];
+    out[c] = (which == SSE_FN_L2_ERROR) ? std::sqrt(s) : s;
+  }
   return 0;
 }
 

@@ -61,7 +61,7 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_time_residual", "sse_kernel_launches", "sse_device_bytes",
            "sse_measure_fp64_peak", "sse_time_derivative_range", "sse_set_stream",
            "sse_upload_state", "sse_download_dudt", "sse_upload_and_nodal_values",
-           "sse_download_dudt_range", "sse_sync_copies"]
+           "sse_download_dudt_range", "sse_sync_copies", "sse_functional"]
 
 
 def load_library(path: Optional[str] = None):
@@ -108,6 +108,7 @@ def load_library(path: Optional[str] = None):
     lib.sse_upload_and_nodal_values.argtypes = [vp, vp]
     lib.sse_download_dudt_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
     lib.sse_sync_copies.argtypes = [vp]
+    lib.sse_functional.argtypes = [vp, C.c_int, C.c_int, vp, c_d_p]
     if path is None:
         _LIB = lib
     return lib
@@ -395,6 +396,26 @@ class DeviceResidual:
 
     def device_bytes(self) -> int:
         return int(self.lib.sse_device_bytes(self.h))
+
+    # ------------------------------------------------------------------ analysis functionals
+    FUNCTIONALS = {"conservation": 0, "entropy": 1, "energy": 2, "energy_residual": 3,
+                   "entropy_residual": 4, "l2_error": 5}
+
+    def functional(self, which: str, arg: str = "state",
+                   exact_q: Optional[np.ndarray] = None) -> np.ndarray:
+        """sse_functional on the device-resident state / last residual (Analysis/conservation.jl
+        :113-190, error.jl:58-91).  ``exact_q``: (N_e, N_c, N_q) host array for ``l2_error``."""
+        kind = self.FUNCTIONALS[which]
+        n_out = 1 if which in ("entropy", "entropy_residual") else self.N_c
+        out = np.zeros(n_out)
+        ptr = None
+        if exact_q is not None:
+            exact_q = _f64(exact_q)
+            assert exact_q.shape == (self.N_e, self.N_c, self.N_q)
+            ptr = exact_q.ctypes.data
+        self._check(self.lib.sse_functional(self.h, kind, 1 if arg == "dudt" else 0, ptr,
+                                            out.ctypes.data_as(c_d_p)), "sse_functional")
+        return out
 
     # ------------------------------------------------------------------ halo
     def halo_setup(self, send_idx: np.ndarray):
