@@ -398,6 +398,46 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   }
 }
 
+// Loop A of scalar conservation laws without entropy projection (standard form, proj == 0):
+// u_q = V u, u_f = R u_q.  One element is a single column for the V / R applies -- far too little
+// work for a CTA -- so NB consecutive elements ride along as "components" (as in
+// k_standard_tensor): table reads, index arithmetic and barriers are amortised over NB elements
+// and the stage-B / stage-A work items fill the warps.
+template <int DIM, int N1, int NB>
+struct NodalBatchCfg {
+  static constexpr int NQ = ipow(N1, DIM);
+  static __host__ __device__ constexpr int region(int Np, int Nf) {
+    return NB * (vtmp_per_column<DIM, N1>() + Np) > NB * Nf ? NB * (vtmp_per_column<DIM, N1>() + Np)
+                                                          : NB * Nf;
+  }
+  static __host__ __device__ constexpr size_t bytes(int Np, int Nf) {
+    return sizeof(double) * (size_t)(NB * NQ + region(Np, Nf));
+  }
+};
+
+template <int DIM, int N1, int LAW, bool COLLAPSED, int NB>
+__global__ void __launch_bounds__(128)
+k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restrict__ u_q,
+                double* __restrict__ u_f) {
+  static_assert(LawTraits<DIM, LAW>::NC == 1, "scalar conservation laws only");
+  constexpr int NQ = ipow(N1, DIM);
+  constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
+  extern __shared__ __align__(16) double sm[];
+  const int Np = T.N_p;
+  double* bufQ = sm;
+  double* tmp = bufQ + NB * NQ;
+  double* bufP = tmp + NB * vtmp_per_column<DIM, N1>();
+  double* bufF = tmp;                      // aliases tmp/bufP once the V apply is done
+  const long long k0 = G.k_begin + (long long)blockIdx.x * NB;
+  const int Ev = (int)min((long long)NB, G.N_e - k0);
+  SSE_LOOP(idx, NB * Np) bufP[idx] = (idx < Ev * Np) ? __ldcg(u + k0 * Np + idx) : 0.0;
+  __syncthreads();
+  apply_V_t<DIM, N1, NB, 1>(vtab(T), bufP, bufQ, tmp);
+  apply_R_t<NQ, NB, 1, Nf, N1>(T, bufQ, bufF);
+  SSE_LOOP(idx, Ev * NQ) u_q[k0 * NQ + idx] = bufQ[idx];
+  SSE_LOOP(idx, Ev * Nf) u_f[k0 * Nf + idx] = bufF[idx];
+}
+
 // ==================================================== loop B, flux-differencing form
 // Compile-time geometry of the specialised loop-B kernel: EL elements per 128-thread CTA,
 // NF facet nodes, and the shared-memory carve-up (in doubles; regions holding double2 start

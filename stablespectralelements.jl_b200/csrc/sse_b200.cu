@@ -209,6 +209,20 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
   constexpr int EL = NodalCfg<DIM, N1>::E;
   if (TensorNF<DIM, N1, true>::value != h->cfg.N_f)
     return fail("facet-node count does not match the specialised kernel");
+  if constexpr (DIM == 3 && LawTraits<DIM, LAW>::NC == 1) {
+    if (h->proj == 0) {   // scalar law, no entropy projection: 8 elements per CTA as components
+      constexpr int NB = 8;
+      const size_t smem = NodalBatchCfg<DIM, N1, NB>::bytes(h->cfg.N_p, h->cfg.N_f);
+      CU(cudaFuncSetAttribute(k_nodal_batched<DIM, N1, LAW, true, NB>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
+      k_nodal_batched<DIM, N1, LAW, true, NB><<<grid, 128, smem, h->stream>>>(h->T, h->G, u_dev,
+                                                                             h->u_q, h->u_f);
+      h->launches++;
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
   const size_t smem = NodalCfg<DIM, N1>::bytes(h->cfg.N_c, h->cfg.N_p, h->cfg.N_f);
   CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
