@@ -42,7 +42,7 @@ static int fail(const char* fmt, ...) {
                   cudaGetErrorString(e_));                                            \
   } while (0)
 
-#define SSE_MAX_CHUNKS 16
+#define SSE_MAX_CHUNKS 32
 
 struct sse_handle {
   sse_config cfg{};
@@ -52,6 +52,12 @@ struct sse_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;          // second copy stream: D2H of finished chunks while
+                                              // later chunks are still being uploaded
+  // host-buffer pipeline: chunk_need[c] = bit mask of the element chunks that hold a neighbour
+  // of chunk c (loop B of c may start once loop A of those chunks is enqueued)
+  int n_chunk = 1;
+  uint32_t chunk_need[SSE_MAX_CHUNKS] = {};
   cudaEvent_t ev_chunk[SSE_MAX_CHUNKS] = {};
   unsigned next_ev = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -354,6 +360,7 @@ int sse_destroy(sse_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   for (auto& e : h->ev_chunk)
     if (e) cudaEventDestroy(e);
   delete h;
@@ -393,6 +400,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   CU(cudaSetDevice(cfg->device));
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
   for (auto& e : h->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
 
@@ -739,10 +747,20 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     h->halo_elems = (cfg->N_halo + Nf - 1) / Nf;
     const int64_t ntr = (int64_t)Nf * (Ne + h->halo_elems);
     std::vector<int> toff((size_t)Nf * Ne), mp((size_t)Nf * Ne);
+    h->n_chunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+    if (h->second_order || cfg->N_halo > 0) h->n_chunk = 1;
+    const int nch = h->n_chunk;
+    auto chunk_of = [&](int64_t k) {   // inverse of lo(c) = Ne*c/nch
+      int c = (int)std::min<int64_t>(nch - 1, (k * nch) / Ne);
+      while (c + 1 < nch && (Ne * (c + 1)) / nch <= k) ++c;
+      while (c > 0 && (Ne * c) / nch > k) --c;
+      return c;
+    };
     for (int64_t g = 0; g < (int64_t)Nf * Ne; ++g) {
       int64_t t = mapP[g];
       if (t < 0 || t >= ntr) return fail("mapP[%lld] = %lld out of range", (long long)g, (long long)t);
       int64_t kp = t / Nf, jp = t % Nf;
+      if (kp < Ne) h->chunk_need[chunk_of(g / Nf)] |= 1u << chunk_of(kp);
       toff[g] = (int)(kp * Nc * Nf + jp);
       mp[g] = (int)t;
     }
@@ -907,13 +925,16 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
     return run_b(h, dudt, rk);
   }
   // Host buffers: pipeline the copies against the kernels in element chunks.  Loop A of chunk c
-  // starts as soon as its slice of u has landed; loop B needs every trace, so it starts after
-  // the last loop A and its chunks are copied back while later chunks still compute.
+  // starts as soon as its slice of u has landed.  Loop B of chunk b reads the traces of b's
+  // neighbours only, so it is enqueued as soon as loop A of every chunk holding such a
+  // neighbour (chunk_need, from mapP) has been enqueued -- on a slab-ordered mesh that is one
+  // chunk behind the upload front -- and its slice of dudt is copied back on a second copy
+  // stream while later chunks are still uploading.  The residual then costs about
+  // max(H2D, compute) instead of H2D + loop B.
   // (Asynchronous only for pinned host memory; pageable memory degrades to staged copies.)
   const int64_t Ne = h->cfg.N_e;
   const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
-  int nchunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
-  if (h->second_order) nchunk = 1;
+  const int nchunk = h->n_chunk;
   auto lo = [&](int c) { return (Ne * c) / nchunk; };
   for (int c = 0; c < nchunk; ++c) {
     CU(cudaMemcpyAsync(h->u + lo(c) * blk, u + lo(c) * blk, (lo(c + 1) - lo(c)) * blk * sizeof(double),
@@ -921,27 +942,34 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
     CU(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
   }
   int rc = 0;
+  uint32_t a_done = 0, b_done = 0;
   for (int c = 0; c < nchunk && !rc; ++c) {
     CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
     h->G.k_begin = lo(c);
     h->G.N_e = lo(c + 1);
     rc = run_a(h, h->u);
-  }
-  for (int c = 0; c < nchunk && !rc; ++c) {
-    h->G.k_begin = lo(c);
-    h->G.N_e = lo(c + 1);
-    rc = run_b(h, h->dudt, rk);
-    if (rc) break;
-    CU(cudaEventRecord(h->ev_chunk[c], h->stream));
-    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[c], 0));
-    CU(cudaMemcpyAsync(dudt + lo(c) * blk, h->dudt + lo(c) * blk,
-                       (lo(c + 1) - lo(c)) * blk * sizeof(double), cudaMemcpyDeviceToHost,
-                       h->copy_stream));
+    a_done |= 1u << c;
+    for (int b = 0; b < nchunk && !rc; ++b) {
+      if ((b_done >> b) & 1u) continue;
+      if ((h->chunk_need[b] | (1u << b)) & ~a_done) continue;   // a neighbour chunk is missing
+      h->G.k_begin = lo(b);
+      h->G.N_e = lo(b + 1);
+      rc = run_b(h, h->dudt, rk);
+      if (rc) break;
+      b_done |= 1u << b;
+      // ev_chunk[b] was consumed by loop A of chunk b (b <= c), so it can be reused
+      CU(cudaEventRecord(h->ev_chunk[b], h->stream));
+      CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_chunk[b], 0));
+      CU(cudaMemcpyAsync(dudt + lo(b) * blk, h->dudt + lo(b) * blk,
+                         (lo(b + 1) - lo(b)) * blk * sizeof(double), cudaMemcpyDeviceToHost,
+                         h->d2h_stream));
+    }
   }
   h->G.k_begin = 0;
   h->G.N_e = Ne;
   if (rc) return -1;
   CU(cudaStreamSynchronize(h->copy_stream));
+  CU(cudaStreamSynchronize(h->d2h_stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }

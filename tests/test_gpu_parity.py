@@ -147,6 +147,36 @@ def test_device_resident_solve_reproduces_reference_golden_l2():
             solver.close()
 
 
+def test_chunked_host_pipeline_matches_device_path():
+    """sse_residual with host buffers pipelines element chunks (H2D / loop A / loop B as soon as
+    the neighbouring chunks' traces exist / D2H on a second stream); the result must be bitwise
+    the device-resident residual.  24 576 elements -> 6 chunks; pinned and pageable buffers."""
+    import torch
+    solver, u0 = cases.euler_tet_case(p=2, M=16, lazy=False, warp=True, ic="periodic")
+    try:
+        u = cases.rough_state(solver, u0, seed=1)
+        h = solver.handle
+        h.set_state(u)
+        h.nodal_values()
+        h.time_derivative()
+        ref = np.empty_like(u)
+        h.download_dudt(ref)
+        h.sync()
+        got = np.full_like(u, np.nan)
+        semi_discrete_residual(got, u, solver, 0.0)              # pageable host memory
+        assert np.array_equal(got, ref)
+        up = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+        dp = torch.empty(u.shape, dtype=torch.float64, pin_memory=True)
+        up.numpy()[...] = u
+        dp.numpy()[...] = np.nan
+        for _ in range(2):                                       # back-to-back calls
+            semi_discrete_residual(dp.numpy(), up.numpy(), solver, 0.0)
+        assert np.array_equal(dp.numpy(), ref)
+        assert np.array_equal(up.numpy(), u)
+    finally:
+        solver.close()
+
+
 def test_error_paths():
     solver, u0 = cases.advection_tri_case(p=2, M=2, lazy=False)
     try:
