@@ -25,6 +25,7 @@ struct Tables {
   const double *wA, *wB, *wC;          // warped-product tables
   const double *wCt;                   // 3-D: C re-ordered [mode][a3]; pair / mode tables (vmap3.cuh)
   const int *pairtab, *modetab;
+  const double *wK;                    // 3-D: fused middle stage of V V^T (vmap3.cuh)
   const int *sig;                      // sigma_i (n1^d), -1 where unused
   const int *R_rp, *R_ci;  const double *R_v;  const int *R_slot;   // R rows -> Rt entry ids
   // arithmetic-progression descriptor of R row j (tensor-product elements; else NULL):

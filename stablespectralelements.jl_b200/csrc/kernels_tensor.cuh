@@ -46,7 +46,7 @@ struct VTab {
 };
 __device__ __forceinline__ VTab vtab(const Tables& T) {
   return VTab{T.wA, T.wB, T.wC, T.Vd, T.VdT, T.sig, T.N_p, T.v_kind,
-              V3Tab{T.wC, T.wCt, T.pairtab, T.modetab}};
+              V3Tab{T.wC, T.wCt, T.pairtab, T.modetab, T.wK}};
 }
 
 // scratch doubles the V / V^T applies need for E elements of NC components
@@ -204,6 +204,26 @@ __device__ __noinline__ void apply_Vt_t(const VTab T, double* __restrict__ src,
   }
 }
 
+// x <- V V^T x in place on the nodal block x [E][NC][NQ] (3-D warped product only): the two
+// ragged b3-contractions around the modal coefficients are fused into one 5-stage pass
+// (A^T, B^T, K, B, A; vmap3.cuh), so the modal intermediate is never formed.
+// tmp: 2 * E * NC * ZS doubles.
+template <int N1, int NC, int E, bool OOL = false>
+__device__ __noinline__ void apply_VtV_t(const VTab T, double* __restrict__ x,
+                                         double* __restrict__ tmp) {
+  double* Z2 = tmp + E * NC * V3Dims<N1>::ZS;
+  vt3_stageA<N1, E * NC>(threadIdx.x, 128, x);
+  __syncthreads();
+  vt3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, x, tmp);
+  __syncthreads();
+  vtv3_stageK<N1, NC, E>(threadIdx.x, 128, T.v3, tmp, Z2);
+  __syncthreads();
+  v3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, Z2, x);
+  __syncthreads();
+  v3_stageA<N1, E * NC>(threadIdx.x, 128, x);
+  __syncthreads();
+}
+
 // dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread.  Rows of R on tensor-product
 // elements touch an arithmetic progression of volume nodes (one tensor line, or the N1 x N1
 // block behind a node of the collapsed face), so no column indices are loaded.
@@ -273,6 +293,34 @@ __device__ __forceinline__ void mass_solve_t(const Tables& T, const Geo& G, long
   apply_Vt_t<DIM, N1, NC, E>(vtab(T), q, rhs, tmp);
 }
 
+// dudt-side epilogue of the loop-B kernels: modal = M^-1 V^T r for the nodal residual r
+// [E][NC][NQ] (destroyed).  With the 3-D warped product and the weight-adjusted solver,
+// M^-1 V^T r = V^T (W/J) (V V^T r): one fused V V^T pass, the scaling, one V^T.
+template <int DIM, int N1, int NC, int E>
+__device__ __forceinline__ void project_and_solve_t(const Tables& T, const Geo& G, long long k0,
+                                                    double* __restrict__ r,
+                                                    double* __restrict__ modal,
+                                                    double* __restrict__ tmp) {
+  constexpr int NQ = ipow(N1, DIM);
+  if constexpr (DIM == 3) {
+    if (T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED && !T.has_Minv) {
+      apply_VtV_t<N1, NC, E>(vtab(T), r, tmp);
+      SSE_LOOP(idx, E * NQ) {
+        int i = idx % NQ, e = idx / NQ;
+        long long k = min(k0 + e, G.N_e - 1);
+        double sc = fdiv(__ldg(T.W + i), G.J_q[k * NQ + i]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r[(e * NC + c) * NQ + i] *= sc;
+      }
+      __syncthreads();
+      apply_Vt_t<DIM, N1, NC, E>(vtab(T), r, modal, tmp);
+      return;
+    }
+  }
+  apply_Vt_t<DIM, N1, NC, E>(vtab(T), r, modal, tmp);
+  mass_solve_t<DIM, N1, NC, E>(T, G, k0, modal, r, tmp);
+}
+
 // =========================================================================== loop A
 // facet nodes of a tensor-product element
 template <int DIM, int N1, bool COLLAPSED>
@@ -294,8 +342,10 @@ struct NodalCfg {
   static constexpr int NQ = ipow(N1, DIM);
   static constexpr int E = (128 / NQ) > 0 ? 128 / NQ : 1;
   static __host__ __device__ constexpr int tmp(int NC) { return E * NC * vtmp_per_column<DIM, N1>(); }
+  static __host__ __device__ constexpr int mx(int a, int b) { return a > b ? a : b; }
+  // the fused V V^T pass needs two Z buffers; the second one overlays bufP, dead by then
   static __host__ __device__ constexpr int region(int NC, int Np, int Nf) {
-    return (tmp(NC) + E * NC * Np) > E * NC * Nf ? (tmp(NC) + E * NC * Np) : E * NC * Nf;
+    return mx(mx(tmp(NC) + E * NC * Np, E * NC * Nf), DIM == 3 ? 2 * tmp(NC) : 0);
   }
   static __host__ __device__ constexpr size_t bytes(int NC, int Np, int Nf) {
     return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf));
@@ -355,7 +405,19 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] = w[c] * sc;
   }
   __syncthreads();
-  if (proj == 2) {
+  if (proj == 2 && DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
+    // projected entropy variables at the volume nodes, V M^-1 V^T (W J w) with
+    // M^-1 = V^T (W/J) V:  two fused V V^T passes around the W/J scaling, no modal intermediate
+    if constexpr (DIM == 3) apply_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp);
+    if (threadIdx.x < E * NQ) {
+      const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
+      const double sc = fdiv(__ldg(T.W + i), jq);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] *= sc;
+    }
+    __syncthreads();
+    if constexpr (DIM == 3) apply_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp);
+  } else if (proj == 2) {
     apply_Vt_t<DIM, N1, NC, E, true>(vtab(T), bufQ, bufP, tmp);
     // mass solve (weight-adjusted, M^-1 = I): V, W/J, V^T -- or the diagonal scaling
     if (T.mass_kind == MASS_DIAGONAL) {
@@ -785,8 +847,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   }
   __syncthreads();
   // ---- phase 6: dudt = M^-1 V^T r_q
-  apply_Vt_t<DIM, N1, NC, EL>(vtab(T), sR, sM, sX);
-  mass_solve_t<DIM, N1, NC, EL>(T, G, k0, sM, sR, sX);
+  project_and_solve_t<DIM, N1, NC, EL>(T, G, k0, sR, sM, sX);
   store_result(T, G, rk, k0, EL, NC, sM, dudt);
 }
 
@@ -955,6 +1016,19 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   }
   __syncthreads();
   // ---- phase 3: dudt = M^-1 V^T r  (the NB elements ride along as NB "components")
+  if (DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
+    // M^-1 V^T r = V^T (W/J) (V V^T r): fused V V^T pass, scaling, one V^T
+    if constexpr (DIM == 3) apply_VtV_t<N1, NB, 1>(vtab(T), sR, sX);
+    SSE_LOOP(idx, NB * NQ) {
+      const int ii = idx % NQ, b = idx / NQ;
+      const long long k = min(k0 + b, G.N_e - 1);
+      sR[idx] *= fdiv(__ldg(T.W + ii), __ldcg(G.J_q + k * NQ + ii));
+    }
+    __syncthreads();
+    apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
+    store_result(T, G, rk, k0, NB, 1, sM, dudt);
+    return;
+  }
   apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
   if (T.mass_kind == MASS_DIAGONAL) {
     SSE_LOOP(idx, NB * NQ) {

@@ -451,7 +451,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       V3HostTables ht;
       if (v3_build_tables(n, ops->sigma_i, ops->warp_C, ht)) {
         if (dev_upload_vec(h, ht.wCt, &T.wCt) || dev_upload_vec(h, ht.pairtab, &T.pairtab) ||
-            dev_upload_vec(h, ht.modetab, &T.modetab))
+            dev_upload_vec(h, ht.modetab, &T.modetab) || dev_upload_vec(h, ht.wK, &T.wK))
           return -1;
       } else {
         h->const_conflict = 1;   // modes not ordered b3-fastest: generic kernels only
@@ -861,7 +861,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   }
   auto smem_a_fast = [&](int E) {
     // upper bound of NodalCfg::bytes (the launch computes the exact figure)
-    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf);
+    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 3 * (size_t)Nc * Nq + (size_t)Nc * Nf);
   };
   auto smem_b_fast = [&](int E) {
     const size_t H = (size_t)h->n1 / 2;

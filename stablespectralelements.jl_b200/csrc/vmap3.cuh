@@ -43,6 +43,7 @@ __constant__ double c_wB[3][125];
 #include <vector>
 struct V3HostTables {
   std::vector<double> wCt;
+  std::vector<double> wK;   // [pair][a3'][a3] = sum_b3 C[a3',pair,b3] C[a3,pair,b3]  (V V^T, middle)
   std::vector<int> pairtab, modetab;
 };
 // sigma [n][n][n] (-1 where unused), wC [a3][b1][b2][b3].  Returns false when the modes are not
@@ -68,6 +69,17 @@ inline bool v3_build_tables(int n, const int* sigma, const double* wC, V3HostTab
     }
   for (int m = 0; m < NP; ++m)
     if (out.modetab[m] < 0) return false;
+  out.wK.assign((size_t)T2 * n * n, 0.0);
+  pr = 0;
+  for (int b1 = 0; b1 < n; ++b1)
+    for (int b2 = 0; b2 < n - b1; ++b2, ++pr)
+      for (int a = 0; a < n; ++a)
+        for (int a3 = 0; a3 < n; ++a3) {
+          double acc = 0.0;
+          for (int b3 = 0; b3 < n - b1 - b2; ++b3)
+            acc += wC[((a * n + b1) * n + b2) * n + b3] * wC[((a3 * n + b1) * n + b2) * n + b3];
+          out.wK[((size_t)pr * n + a) * n + a3] = acc;
+        }
   return true;
 }
 
@@ -78,6 +90,7 @@ struct V3Tab {
   const double* wCt;   // [mode][a3]  (= C[a3][b1][b2][b3] of that mode)
   const int* pairtab;  // [pair] b1 | b2 << 4 | s0 << 8
   const int* modetab;  // [mode] pair
+  const double* wK;    // [pair][a3'][a3]: stage C of V^T followed by stage C of V, fused
 };
 
 template <int N1> struct V3Dims {
@@ -262,6 +275,31 @@ SSE_HD void vt3_stageC(int tid, int nthr, V3Tab T, const double* Z, double* dst)
 #pragma unroll
     for (int a3 = 0; a3 < N1; ++a3) acc = fma(SSE_LDG(cb + a3), zb[a3], acc);
     dst[idx] = acc;
+  }
+}
+
+// ---- V V^T, fused middle: the two ragged b3-contractions around the modal coefficients collapse
+// to one n x n matrix per pair, Z2[ec][pair][a3'] = sum_a3 K[pair][a3'][a3] Z[ec][pair][a3].
+// One work item per (pair, a3'), all components in registers (as in stage C of V).
+template <int N1, int NC, int E>
+SSE_HD void vtv3_stageK(int tid, int nthr, V3Tab T, const double* Z, double* Z2) {
+  using D = V3Dims<N1>;
+  for (int idx = tid; idx < E * D::ZS; idx += nthr) {
+    const int a = idx % N1, pr = (idx / N1) % D::T2, e = idx / D::ZS;
+    const double* kb = T.wK + (pr * N1 + a) * N1;
+    const double* zb = Z + e * NC * D::ZS + pr * N1;
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+#pragma unroll
+    for (int a3 = 0; a3 < N1; ++a3) {
+      const double v = SSE_LDG(kb + a3);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = fma(v, zb[c * D::ZS + a3], acc[c]);
+    }
+    double* ob = Z2 + e * NC * D::ZS + pr * N1 + a;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) ob[c * D::ZS] = acc[c];
   }
 }
 

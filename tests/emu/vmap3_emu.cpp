@@ -11,7 +11,14 @@ using namespace sse;
 template <int N1, int NC, int E>
 static void run(int transpose, V3Tab T, double* src, double* dst, double* Z, int nthr) {
   constexpr int EC = E * NC;
-  if (!transpose) {
+  if (transpose == 2) {          // x <- V V^T x in place, Z and Z2 = Z + EC*ZS as scratch
+    double* Z2 = Z + EC * V3Dims<N1>::ZS;
+    for (int t = 0; t < nthr; ++t) vt3_stageA<N1, EC>(t, nthr, src);
+    for (int t = 0; t < nthr; ++t) vt3_stageB<N1, EC>(t, nthr, src, Z);
+    for (int t = 0; t < nthr; ++t) vtv3_stageK<N1, NC, E>(t, nthr, T, Z, Z2);
+    for (int t = 0; t < nthr; ++t) v3_stageB<N1, EC>(t, nthr, Z2, src);
+    for (int t = 0; t < nthr; ++t) v3_stageA<N1, EC>(t, nthr, src);
+  } else if (!transpose) {
     for (int t = 0; t < nthr; ++t) v3_stageC<N1, NC, E>(t, nthr, T, src, Z);
     for (int t = 0; t < nthr; ++t) v3_stageB<N1, EC>(t, nthr, Z, dst);
     for (int t = 0; t < nthr; ++t) v3_stageA<N1, EC>(t, nthr, dst);
@@ -29,7 +36,7 @@ extern "C" int vmap3_emu(int n1, int nc, int e, int transpose, const double* wA,
   std::memcpy(c_wB[n1 - 3], wB, sizeof(double) * n1 * n1 * n1);
   V3HostTables ht;
   if (!v3_build_tables(n1, sigma, wC, ht)) return -2;
-  V3Tab T{wC, ht.wCt.data(), ht.pairtab.data(), ht.modetab.data()};
+  V3Tab T{wC, ht.wCt.data(), ht.pairtab.data(), ht.modetab.data(), ht.wK.data()};
 #define CASE(N, C, EE) if (n1 == N && nc == C && e == EE) { run<N, C, EE>(transpose, T, src, dst, Z, nthr); return 0; }
   CASE(5, 5, 1) CASE(5, 1, 1) CASE(5, 4, 1) CASE(4, 5, 2) CASE(4, 1, 2) CASE(3, 5, 4) CASE(3, 1, 4)
   CASE(4, 4, 1) CASE(3, 4, 1)

@@ -39,7 +39,7 @@ def test_vmap3_stages_match_dense_V(emu, p, nc, e, nthr):
     A = np.ascontiguousarray(V.A); B = np.ascontiguousarray(V.B); C = np.ascontiguousarray(V.C)
     rng = np.random.default_rng(p * 10 + nc)
     ZS = n * n * (n + 1) // 2
-    Z = np.zeros(e * nc * ZS)
+    Z = np.zeros(2 * e * nc * ZS)
     # V
     x = rng.standard_normal((e * nc, Np))
     src = x.copy().ravel(); dst = np.zeros(e * nc * Nq)
@@ -56,3 +56,11 @@ def test_vmap3_stages_match_dense_V(emu, p, nc, e, nthr):
     assert rc == 0
     ref = y @ Vd
     assert np.max(np.abs(dst.reshape(e * nc, Np) - ref)) < 1e-13 * np.max(np.abs(ref))
+    # V V^T in place (fused middle stage)
+    y2 = rng.standard_normal((e * nc, Nq))
+    src = y2.copy().ravel(); dst = np.zeros(1)
+    rc = emu.vmap3_emu(n, nc, e, 2, _ptr(A), _ptr(B), _ptr(C), _ptr(sig, ctypes.c_int),
+                       _ptr(src), _ptr(dst), _ptr(Z), nthr)
+    assert rc == 0
+    ref = y2 @ Vd @ Vd.T
+    assert np.max(np.abs(src.reshape(e * nc, Nq) - ref)) < 1e-13 * np.max(np.abs(ref))
