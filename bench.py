@@ -142,6 +142,12 @@ def main():
             cpu_reference_arm(args)
         return
 
+    # native libraries (NCCL prints a version banner) must not write to stdout: the driver reads
+    # ONE JSON line from it.  Route fd 1 to stderr until the line is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -269,7 +275,10 @@ def main():
             res = cpu_baseline.run(M=args.cpu_m, warp=not args.straight, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": res["value"], "unit": "DOF/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"]}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dres.close()
     if world > 1:
         dist.barrier()
