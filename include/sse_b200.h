@@ -174,6 +174,35 @@ int sse_measure_fp64_peak(int device, double* tflops);
 int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
 int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
 
+/* ---- on-device geometric factors ----------------------------------------------
+ * GeometricFactors(mesh, reference_element, metric_type) of SpatialDiscretizations/mesh.jl:213-509
+ * evaluated on the device from the mapping-node coordinates: ExactMetrics (d = 1, 2, 3; optional
+ * Jacobian projection, SpatialDiscretizations.jl:311-318) and ConservativeCurlMetrics in 3-D
+ * (Tet: curl form on the degree-(N+1) nodes, mesh.jl:413-509; Hex: P = NULL).  The result holds
+ * DEVICE pointers; sse_create accepts them in place of host arrays (it copies device to device);
+ * release with sse_geometry_free.  All matrices row-major, host or device memory.             */
+enum sse_metric_type { SSE_METRIC_EXACT = 0, SSE_METRIC_CONSERVATIVE_CURL = 1 };
+typedef struct {
+  int32_t dim, metric;
+  int32_t N_map, N_map1;     /* mapping nodes of degree N and (curl form, Tet) N+1              */
+  int32_t N_q, N_f;
+  int64_t N_e;
+  const double* D[3];        /* (N_map x N_map) d/dr_n on the mapping nodes (RefElemData.Drst)  */
+  const double* Vq;          /* (N_q x N_map) mapping nodes -> volume quadrature nodes          */
+  const double* Vf;          /* (N_f x N_map) mapping nodes -> facet quadrature nodes           */
+  const double* P;           /* curl: (N_map1 x N_map) degree N -> N+1, NULL = identity         */
+  const double* D1[3];       /* curl: (N_map1 x N_map1)                                         */
+  const double* Vq1;         /* curl: (N_q x N_map1)                                            */
+  const double* Vf1;         /* curl: (N_f x N_map1)                                            */
+  const double* nrstJ;       /* (N_f x d) scaled reference normals at the facet nodes           */
+  const double* Jproj;       /* exact: (N_q x N_q) L2 projection of J, or NULL                  */
+  const double* xyz[3];      /* (N_map, N_e) mapping-node coordinates (mesh.xyz), Julia layout  */
+  int32_t device;
+} sse_mapping;
+int sse_geometry_build(const sse_mapping* m, sse_geometry* out_device_pointers);
+int sse_geometry_free(sse_geometry* g);
+int sse_copy_to_host(void* dst_host, const void* src_dev, int64_t bytes);
+
 /* ---- analysis functionals on the device --------------------------------------
  * Analysis/conservation.jl:113-190 (evaluate_conservation, evaluate_conservation_residual for the
  * PrimaryConservation / EnergyConservation / EntropyConservation analyses) and

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "kernels_tensor.cuh"
 #include "functionals.cuh"
+#include "geometry.cuh"
 
 using namespace sse;
 
@@ -93,7 +94,8 @@ static int dev_upload(sse_handle* h, const Tp* src, size_t n, Tp** out) {
   CU(cudaMalloc(&p, n * sizeof(Tp)));
   h->allocs.push_back(p);
   h->bytes += (int64_t)(n * sizeof(Tp));
-  if (src) CU(cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+  // cudaMemcpyDefault: the source may be host memory or (sse_geometry_build) device memory
+  if (src) CU(cudaMemcpy(p, src, n * sizeof(Tp), cudaMemcpyDefault));
   else CU(cudaMemset(p, 0, n * sizeof(Tp)));
   *out = (Tp*)p;
   return 0;
@@ -1214,6 +1216,97 @@ int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host
     for (int b = 0; b < nblk; ++b) s += hb[(size_t)b * n_out + c];
     out[c] = (which == SSE_FN_L2_ERROR) ? std::sqrt(s) : s;
   }
+  return 0;
+}
+
+// ---- on-device geometric factors (geometry.cuh)
+int sse_geometry_build(const sse_mapping* m, sse_geometry* out) {
+  if (!m || !out) return fail("null argument");
+  std::memset(out, 0, sizeof(*out));
+  const int d = m->dim, Nm = m->N_map, Nq = m->N_q, Nf = m->N_f;
+  const int64_t Ne = m->N_e;
+  if (d < 1 || d > 3 || Nm < 1 || Nq < 1 || Nf < 1 || Ne < 1) return fail("bad mapping sizes");
+  const bool curl = m->metric == SSE_METRIC_CONSERVATIVE_CURL;
+  if (curl && d != 3) return fail("the conservative curl form is implemented on the device for d = 3 only");
+  const int Nm1 = curl ? (m->P ? m->N_map1 : Nm) : Nm;
+  if (!m->Vq || !m->Vf || !m->nrstJ) return fail("mapping operators missing");
+  for (int n = 0; n < d; ++n)
+    if (!m->D[n] || !m->xyz[n]) return fail("mapping operators missing");
+  if (curl && (!m->D1[0] || !m->D1[1] || !m->D1[2] || !m->Vq1 || !m->Vf1))
+    return fail("degree-(N+1) operators missing for the curl form");
+  CU(cudaSetDevice(m->device));
+  std::vector<void*> tmp;
+  auto up = [&](const double* src, size_t n, const double** dst) -> int {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) return fail("out of device memory");
+    tmp.push_back(p);
+    if (cudaMemcpy(p, src, n * sizeof(double), cudaMemcpyDefault) != cudaSuccess)
+      return fail("copy of the mapping data failed");
+    *dst = (const double*)p;
+    return 0;
+  };
+  MapOps M{};
+  M.Nm = Nm; M.Nm1 = Nm1; M.Nq = Nq; M.Nf = Nf;
+  int rc = 0;
+  for (int n = 0; n < d && !rc; ++n) {
+    rc = up(m->D[n], (size_t)Nm * Nm, &M.D[n]);
+    if (!rc) rc = up(m->xyz[n], (size_t)Nm * Ne, &M.xyz[n]);
+    if (!rc && curl) rc = up(m->D1[n], (size_t)Nm1 * Nm1, &M.D1[n]);
+  }
+  if (!rc) rc = up(m->Vq, (size_t)Nq * Nm, &M.Vq);
+  if (!rc) rc = up(m->Vf, (size_t)Nf * Nm, &M.Vf);
+  if (!rc) rc = up(m->nrstJ, (size_t)Nf * d, &M.nrstJ);
+  if (!rc && curl && m->P) rc = up(m->P, (size_t)Nm1 * Nm, &M.P);
+  if (!rc && curl) rc = up(m->Vq1, (size_t)Nq * Nm1, &M.Vq1);
+  if (!rc && curl) rc = up(m->Vf1, (size_t)Nf * Nm1, &M.Vf1);
+  if (!rc && !curl && m->Jproj) rc = up(m->Jproj, (size_t)Nq * Nq, &M.Jproj);
+  double *Jq = nullptr, *Lq = nullptr, *Jf = nullptr, *nJ = nullptr;
+  if (!rc && (cudaMalloc(&Jq, (size_t)Nq * Ne * sizeof(double)) != cudaSuccess ||
+              cudaMalloc(&Lq, (size_t)Nq * d * d * Ne * sizeof(double)) != cudaSuccess ||
+              cudaMalloc(&Jf, (size_t)Nf * Ne * sizeof(double)) != cudaSuccess ||
+              cudaMalloc(&nJ, (size_t)d * Nf * Ne * sizeof(double)) != cudaSuccess))
+    rc = fail("out of device memory for the geometric factors");
+  if (!rc) {
+    if (curl) {
+      const size_t smem = sizeof(double) * ((size_t)13 * Nm + (size_t)24 * Nm1);
+      cudaFuncSetAttribute(k_geometry_curl3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_geometry_curl3d<<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+    } else {
+      const size_t smem = sizeof(double) * ((size_t)(d + d * d) * Nm + Nq);
+      if (d == 1) {
+        cudaFuncSetAttribute(k_geometry_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_geometry_exact<1><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+      } else if (d == 2) {
+        cudaFuncSetAttribute(k_geometry_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_geometry_exact<2><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+      } else {
+        cudaFuncSetAttribute(k_geometry_exact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_geometry_exact<3><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+      }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail("geometry kernel: %s", cudaGetErrorString(e));
+  }
+  for (void* p : tmp) cudaFree(p);
+  if (rc) {
+    cudaFree(Jq); cudaFree(Lq); cudaFree(Jf); cudaFree(nJ);
+    return rc;
+  }
+  out->J_q = Jq; out->Lambda_q = Lq; out->J_f = Jf; out->nJf = nJ;
+  return 0;
+}
+
+int sse_geometry_free(sse_geometry* g) {
+  if (!g) return 0;
+  cudaFree((void*)g->J_q); cudaFree((void*)g->Lambda_q);
+  cudaFree((void*)g->J_f); cudaFree((void*)g->nJf);
+  g->J_q = g->Lambda_q = g->J_f = g->nJf = nullptr;
+  return 0;
+}
+
+int sse_copy_to_host(void* dst_host, const void* src_dev, int64_t bytes) {
+  if (!dst_host || !src_dev || bytes < 0) return fail("bad argument");
+  CU(cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
   return 0;
 }
 

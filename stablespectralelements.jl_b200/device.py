@@ -54,6 +54,15 @@ class SseGeometry(C.Structure):
                 ("VOL", c_d_p), ("FAC", c_d_p), ("Minv_elem", c_d_p)]
 
 
+class SseMapping(C.Structure):
+    """sse_mapping (include/sse_b200.h): inputs of the on-device GeometricFactors."""
+    _fields_ = [("dim", C.c_int32), ("metric", C.c_int32), ("N_map", C.c_int32),
+                ("N_map1", C.c_int32), ("N_q", C.c_int32), ("N_f", C.c_int32),
+                ("N_e", C.c_int64), ("D", c_d_p * 3), ("Vq", c_d_p), ("Vf", c_d_p), ("P", c_d_p),
+                ("D1", c_d_p * 3), ("Vq1", c_d_p), ("Vf1", c_d_p), ("nrstJ", c_d_p),
+                ("Jproj", c_d_p), ("xyz", c_d_p * 3), ("device", C.c_int32)]
+
+
 EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_residual",
            "sse_nodal_values", "sse_time_derivative", "sse_set_state", "sse_get_state",
            "sse_state_ptr", "sse_rk_stage", "sse_rk_step_ck54", "sse_halo_setup",
@@ -61,7 +70,8 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_time_residual", "sse_kernel_launches", "sse_device_bytes",
            "sse_measure_fp64_peak", "sse_time_derivative_range", "sse_set_stream",
            "sse_upload_state", "sse_download_dudt", "sse_upload_and_nodal_values",
-           "sse_download_dudt_range", "sse_sync_copies", "sse_functional"]
+           "sse_download_dudt_range", "sse_sync_copies", "sse_functional",
+           "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host"]
 
 
 def load_library(path: Optional[str] = None):
@@ -109,6 +119,9 @@ def load_library(path: Optional[str] = None):
     lib.sse_download_dudt_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
     lib.sse_sync_copies.argtypes = [vp]
     lib.sse_functional.argtypes = [vp, C.c_int, C.c_int, vp, c_d_p]
+    lib.sse_geometry_build.argtypes = [C.POINTER(SseMapping), C.POINTER(SseGeometry)]
+    lib.sse_geometry_free.argtypes = [C.POINTER(SseGeometry)]
+    lib.sse_copy_to_host.argtypes = [vp, vp, C.c_int64]
     if path is None:
         _LIB = lib
     return lib
@@ -259,10 +272,19 @@ class DeviceResidual:
             ops.Minv = _dp(Mi)
 
         geo = SseGeometry()
-        Jq, Lq = _f64(gf.J_q[sel]), _f64(gf.Lambda_q[sel])
-        Jf, nJf = _f64(gf.J_f[sel]), _f64(gf.nJf[sel])
-        self._keep += [Jq, Lq, Jf, nJf]
-        geo.J_q, geo.Lambda_q, geo.J_f, geo.nJf = _dp(Jq), _dp(Lq), _dp(Jf), _dp(nJf)
+        on_device = getattr(gf, "on_device", False) and elements is None
+        if on_device:
+            # geometric factors built on the device (sse_geometry_build): hand the device
+            # pointers over, nothing crosses PCIe
+            geo.J_q, geo.Lambda_q, geo.J_f, geo.nJf = gf.device_pointers()
+            Jq = None
+        else:
+            Jq, Lq = _f64(gf.J_q[sel]), _f64(gf.Lambda_q[sel])
+            Jf, nJf = _f64(gf.J_f[sel]), _f64(gf.nJf[sel])
+            self._keep += [Jq, Lq, Jf, nJf]
+            geo.J_q, geo.Lambda_q, geo.J_f, geo.nJf = _dp(Jq), _dp(Lq), _dp(Jf), _dp(nJf)
+        if Jq is None and (form["strategy"] == "physical" or solver.mass_kind == "cholesky"):
+            Jq = _f64(gf.J_q[sel])       # these host-side builders need J_q (downloads it once)
         if form["strategy"] == "physical":
             VOL, FAC = physical_operators(solver)
             VOL, FAC = _f64(VOL[sel]), _f64(FAC[sel])

@@ -176,6 +176,120 @@ def geometric_factors_curl(mesh: MeshData, re: RefElemData) -> GeometricFactors:
     return GeometricFactors(np.ascontiguousarray(J_q), Lambda_q, J_f, nJf, _n_ref(re))
 
 
+class DeviceGeometricFactors:
+    """GeometricFactors evaluated and kept on the device (``sse_geometry_build``, SURVEY.md §8f
+    item 2; mesh.jl:213-509).  ``sse_create`` takes the device pointers directly; host copies of
+    the arrays (same layouts as ``GeometricFactors``) are downloaded lazily, only if some host-side
+    consumer (initial-data projection, the test oracle) asks for them."""
+    on_device = True
+
+    def __init__(self, lib, geo, shapes, n_ref):
+        self._lib, self._geo, self._shapes, self.n_ref = lib, geo, shapes, n_ref
+        self._host = {}
+
+    def device_pointers(self):
+        g = self._geo
+        return g.J_q, g.Lambda_q, g.J_f, g.nJf
+
+    def _fetch(self, name):
+        if name not in self._host:
+            import ctypes as C
+            out = np.empty(self._shapes[name])
+            ptr = C.cast(getattr(self._geo, name), C.c_void_p)
+            if self._lib.sse_copy_to_host(out.ctypes.data, ptr, out.nbytes) != 0:
+                raise RuntimeError("sse_copy_to_host failed: " + self._lib.sse_last_error().decode())
+            self._host[name] = out
+        return self._host[name]
+
+    J_q = property(lambda self: self._fetch("J_q"))
+    Lambda_q = property(lambda self: self._fetch("Lambda_q"))
+    J_f = property(lambda self: self._fetch("J_f"))
+    nJf = property(lambda self: self._fetch("nJf"))
+
+    def nJq(self):
+        return np.einsum("knmi,fm->kifn", self.Lambda_q, self.n_ref)
+
+    def free(self):
+        if self._geo is not None:
+            self._lib.sse_geometry_free(self._geo)
+            self._geo = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def jacobian_projection_matrix(V, W):
+    """SpatialDiscretizations.jl:311-318 as an (N_q x N_q) matrix acting on J_q."""
+    VDM = V.to_dense()
+    return VDM @ np.linalg.solve(VDM.T @ (W[:, None] * VDM), VDM.T * W[None, :])
+
+
+def geometric_factors_device(mesh: MeshData, re: RefElemData, metric_type=None, Jproj=None,
+                             device: int = 0) -> DeviceGeometricFactors:
+    """Same quantities as ``make_geometric_factors`` but evaluated by the CUDA library from the
+    mapping-node coordinates (no CPU fallback: raises if the library or a GPU is missing)."""
+    import ctypes as C
+    from . import device as dev
+    lib = dev.load_library()
+    d = re.dim
+    elem = re.element_type
+    exact = metric_type is None or isinstance(metric_type, ExactMetrics)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    keep = []
+
+    def put(a):
+        a = f64(a)
+        keep.append(a)
+        return dp(a)
+
+    m = dev.SseMapping()
+    m.dim, m.device = d, device
+    m.N_q, m.N_f = re.Vq.shape[0], re.Vf.shape[0]
+    m.N_e = mesh.N_e
+    m.N_map = m.N_map1 = re.Vq.shape[1]
+    for n in range(d):
+        m.D[n] = put(re.Drst[n])
+        m.xyz[n] = put(np.asarray(mesh.xyz[n]).T)          # (N_e, N_map) == Julia (N_map, N_e)
+    m.Vq, m.Vf = put(re.Vq), put(re.Vf)
+    m.nrstJ = put(np.stack(re.nrstJ, axis=1))
+    if exact or d == 1:
+        m.metric = 0
+        if Jproj is not None:
+            m.Jproj = put(Jproj)
+    else:
+        if d != 3:
+            raise NotImplementedError("device curl-form metrics are implemented for d = 3")
+        m.metric = 1
+        if isinstance(elem, Tet):
+            N = re.N
+            r1, s1, t1 = nd.nodes_tet(N + 1)
+            V1, Vr1, Vs1, Vt1 = poly.simplex_basis_3d(N + 1, r1, s1, t1, grad=True)
+            N_to_Np1 = np.linalg.solve(re.VDM.T, vandermonde(elem, N, r1, s1, t1).T).T
+            Np1_to_N = np.linalg.solve(V1.T, vandermonde(elem, N + 1, *re.rst).T).T
+            m.N_map1 = V1.shape[0]
+            m.P = put(N_to_Np1)
+            for n, g in enumerate((Vr1, Vs1, Vt1)):
+                m.D1[n] = put(np.linalg.solve(V1.T, g.T).T)
+            m.Vq1, m.Vf1 = put(re.Vq @ Np1_to_N), put(re.Vf @ Np1_to_N)
+        elif isinstance(elem, Hex):
+            for n in range(3):
+                m.D1[n] = m.D[n]
+            m.Vq1, m.Vf1 = m.Vq, m.Vf
+        else:
+            raise TypeError(elem)
+    geo = dev.SseGeometry()
+    if lib.sse_geometry_build(C.byref(m), C.byref(geo)) != 0:
+        raise RuntimeError("sse_geometry_build failed: " + lib.sse_last_error().decode())
+    N_e, N_q, N_f = mesh.N_e, int(m.N_q), int(m.N_f)
+    shapes = {"J_q": (N_e, N_q), "Lambda_q": (N_e, d, d, N_q), "J_f": (N_e, N_f),
+              "nJf": (N_e, N_f, d)}
+    return DeviceGeometricFactors(lib, geo, shapes, _n_ref(re))
+
+
 def make_geometric_factors(mesh, re, metric_type=None) -> GeometricFactors:
     if metric_type is None or isinstance(metric_type, ExactMetrics):
         return geometric_factors_exact(mesh, re)
@@ -206,16 +320,24 @@ class SpatialDiscretization:
 
 
 def make_spatial_discretization(mesh: MeshData, ra: ReferenceApproximation, metric_type=None,
-                                project_jacobian_flag: Optional[bool] = None
+                                project_jacobian_flag: Optional[bool] = None,
+                                device_geometry: Optional[int] = None
                                 ) -> SpatialDiscretization:
     """``SpatialDiscretization(mesh, ra[, metric_type]; project_jacobian=true)``.
 
     ExactMetrics projects the Jacobian by default; the ChanWilcox constructor never does
     (SpatialDiscretizations.jl:334-393)."""
     exact = metric_type is None or isinstance(metric_type, ExactMetrics)
-    gf = make_geometric_factors(mesh, ra.reference_element, metric_type)
     if project_jacobian_flag is None:
         project_jacobian_flag = exact
+    if device_geometry is not None:
+        # ``device_geometry`` = CUDA device index: evaluate the geometric factors there
+        Jproj = (jacobian_projection_matrix(ra.V, ra.W) if exact and project_jacobian_flag
+                 else None)
+        gf = geometric_factors_device(mesh, ra.reference_element, metric_type, Jproj,
+                                      device_geometry)
+        return SpatialDiscretization(mesh, ra, gf)
+    gf = make_geometric_factors(mesh, ra.reference_element, metric_type)
     if exact and project_jacobian_flag:
         gf.J_q = project_jacobian(gf.J_q, ra.V, ra.W)
     return SpatialDiscretization(mesh, ra, gf)

@@ -69,7 +69,7 @@ def advection_tet_case(p=4, M=2, lazy=True, warp=0.1, mapping_degree=None):
 
 
 def euler_tet_case(p=4, M=2, lazy=True, warp=False, interface="lf", ic="tgv",
-                   approx="modal", shard=None):
+                   approx="modal", shard=None, device_geometry=None):
     """BASELINE config 4 (north star): 3-D Euler Taylor-Green vortex on tetrahedra, flux
     differencing, entropy-conservative two-point flux, LF or EC interface flux."""
     g = 1.4
@@ -84,9 +84,10 @@ def euler_tet_case(p=4, M=2, lazy=True, warp=False, interface="lf", ic="tgv",
         mesh = mesh_subset(mesh, *element_ranges(mesh.N_e, shard[1])[shard[0]])
     if warp:
         mesh = warp_mesh(mesh, ra, ChanWarping(1 / 16, (L, L, L)))
-        sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
+        sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics(),
+                                         device_geometry=device_geometry)
     else:
-        sd = make_spatial_discretization(mesh, ra)
+        sd = make_spatial_discretization(mesh, ra, device_geometry=device_geometry)
     flux = LaxFriedrichsNumericalFlux() if interface == "lf" else EntropyConservativeNumericalFlux()
     solver = Solver(law, sd, FluxDifferencingForm(inviscid_numerical_flux=flux),
                     ReferenceOperator(), lazy=lazy)
