@@ -93,10 +93,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(M, warp, lazy=True, shard=None):
+def build_problem(M, warp, lazy=True, shard=None, device_geometry=None):
     import cases
     return cases.euler_tet_case(p=4, M=M, lazy=lazy, warp=warp, interface="lf", ic="tgv",
-                                shard=shard)
+                                shard=shard, device_geometry=device_geometry)
 
 
 def cpu_reference_arm(args):
@@ -131,6 +131,8 @@ def main():
     ap.add_argument("--cpu-m", type=int, default=16, help="mesh size of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-geometry", action="store_true",
+                    help="evaluate the geometric factors on the GPU (sse_geometry_build) at setup")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,7 +170,8 @@ def main():
     t_setup = time.time()
     # every rank builds the (cheap) global connectivity but only its own shard's geometry
     solver, u0 = build_problem(args.M, warp=not args.straight, lazy=True,
-                               shard=(rank, world) if world > 1 else None)
+                               shard=(rank, world) if world > 1 else None,
+                               device_geometry=local_rank if args.device_geometry else None)
     N_e = solver.spatial_discretization.mesh.mapP.shape[1]
     N_c, N_p = u0.shape[1], u0.shape[2]
     dof = N_e * N_c * N_p
@@ -251,6 +254,7 @@ def main():
                 "parallelism": f"element-sharded x{world}, facet-trace halo over NCCL",
                 "l2": "inputs (6.5 GB geometry + state) far exceed the 126 MB L2; no flush needed",
                 "setup_s": round(t_setup, 1),
+                "geometry": "device (sse_geometry_build)" if args.device_geometry else "host",
             },
             "roofline": {
                 "kernel": "k_fluxdiff_tensor<3,5,Euler,collapsed,8> (loop B: interface flux + "
