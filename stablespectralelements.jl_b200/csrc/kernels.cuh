@@ -32,6 +32,14 @@ struct Tables {
   // columns start + q*stride, q < count; ELL slot k of this facet node in the rows of R^T.
   // packed start | stride << 10 | count << 20 | k << 27
   const int *R_desc;
+  // separable collapsed-face rows (tensor-product simplices): a row of R with N1^2 entries is
+  // rank one, R[j][a2*N1+a3] = R_E[j][a2] * R_r3[a3]; rows with the same start share the inner
+  // contraction.  R_ng = number of distinct starts (0: not separable), R_gstart[g] = start,
+  // R_grp[j] = group of row j.
+  int R_ng;
+  const int *R_gstart, *R_grp;
+  const double *R_E;
+  double R_r3[8];
   const int *Rt_rp, *Rt_ci; const double *Rt_v; const double *C_v;  // R^T rows; C = R^T B
   const int *S_rp, *S_ci;  const double *S_v;                       // S_v[e*dim + m]
   const int *D_rp[3], *D_ci[3];  const double *D_v[3];
@@ -46,6 +54,7 @@ struct Geo {
   const int *toff;      // trace offset of the exterior node: (k'*N_c)*N_f + j'
   const int *mapP;      // raw linear index j' + N_f*k'
   const double *VOL, *FAC, *Minv_e;
+  int pf_dist;          // elements ahead whose inputs a CTA prefetches into L2 (0 = off)
 };
 
 struct RK {

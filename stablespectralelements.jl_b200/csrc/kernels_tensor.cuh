@@ -227,9 +227,27 @@ __device__ __noinline__ void apply_VtV_t(const VTab T, double* __restrict__ x,
 // dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread.  Rows of R on tensor-product
 // elements touch an arithmetic progression of volume nodes (one tensor line, or the N1 x N1
 // block behind a node of the collapsed face), so no column indices are loaded.
+// scratch doubles apply_R_t needs per column for the separable collapsed-face rows
+template <int N1> __host__ __device__ constexpr int rsep_per_column() { return N1 * N1; }
+
 template <int NQ, int NC, int E, int Nf, int N1>
 __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restrict__ src,
-                                          double* __restrict__ dst) {
+                                          double* __restrict__ dst, double* __restrict__ tsc) {
+  // Collapsed face: R[(f1,f2)][a1=f1][a2][a3] = E[f2][a2] r3[a3] (Kronecker factors of
+  // tensor_simplex.jl:221-306), so the a3-contraction is shared by the N1 rows of a group:
+  // 2 * N1 instead of N1^2 terms per row, and every row of R costs the same.
+  const int ng = T.R_ng;
+  if (ng > 0) {
+    SSE_LOOP(idx, E * NC * ng * N1) {
+      const int a2 = idx % N1, g = (idx / N1) % ng, ec = idx / (N1 * ng);
+      const double* s0 = src + ec * NQ + __ldg(T.R_gstart + g) + a2 * N1;
+      double acc = 0.0;
+#pragma unroll
+      for (int a3 = 0; a3 < N1; ++a3) acc = fma(T.R_r3[a3], s0[a3], acc);
+      tsc[idx] = acc;
+    }
+    __syncthreads();
+  }
   SSE_LOOP(idx, E * Nf) {
     int j = idx % Nf, e = idx / Nf;
     double acc[NC];
@@ -245,6 +263,14 @@ __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restr
         double v = __ldg(T.R_v + b + q);
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
+      }
+    } else if (ng > 0 && cnt == N1 * N1 && stride == 1) {
+      const double* t0 = tsc + (e * NC * ng + __ldg(T.R_grp + j)) * N1;
+#pragma unroll
+      for (int a2 = 0; a2 < N1; ++a2) {
+        double v = __ldg(T.R_E + j * N1 + a2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = fma(v, t0[c * ng * N1 + a2], acc[c]);
       }
     } else if (cnt == N1 * N1 && stride == 1) {
 #pragma unroll
@@ -348,7 +374,7 @@ struct NodalCfg {
     return mx(mx(tmp(NC) + E * NC * Np, E * NC * Nf), DIM == 3 ? 2 * tmp(NC) : 0);
   }
   static __host__ __device__ constexpr size_t bytes(int NC, int Np, int Nf) {
-    return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf));
+    return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf) + E * NC * rsep_per_column<N1>());
   }
 };
 
@@ -371,9 +397,20 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   double* tmp = bufQ + E * NC * NQ;
   double* bufP = tmp + Cf::tmp(NC);
   double* bufF = tmp;                      // aliases tmp/bufP; live only after the last apply
+  double* rsc = tmp + Cf::region(NC, Np, Nf);   // scratch of the separable rows of R
   const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
+  if (G.pf_dist > 0) {   // L2 prefetch for the CTA one wave ahead (see k_fluxdiff_tensor)
+    const long long kp = k0 + G.pf_dist;
+    if (kp + E <= G.N_e) {
+      for (int o = threadIdx.x * 128; o < E * NC * Np * 8; o += 128 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(u + kp * NC * Np) + o));
+      if (proj == 2)
+        for (int o = threadIdx.x * 128; o < E * NQ * 8; o += 128 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(G.J_q + kp * NQ) + o));
+    }
+  }
   // own node's Jacobian for the two weightings of the projection (thread = volume node)
   double jq = 1.0;
   if (proj == 2 && threadIdx.x < E * NQ) {
@@ -384,7 +421,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   __syncthreads();
   apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
-    apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
+    apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF, rsc);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
     SSE_LOOP(idx, Ev * NC * Nf) u_f[k0 * NC * Nf + idx] = bufF[idx];
     return;
@@ -440,7 +477,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     }
     apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   }
-  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF);
+  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF, rsc);
   // entropy -> conservative variables at the volume nodes (modal case) and the facet nodes,
   // one loop so the log/exp sequence is instantiated once
   const int nvol = (proj == 2) ? Ev * NQ : 0;
@@ -473,7 +510,7 @@ struct NodalBatchCfg {
                                                           : NB * Nf;
   }
   static __host__ __device__ constexpr size_t bytes(int Np, int Nf) {
-    return sizeof(double) * (size_t)(NB * NQ + region(Np, Nf));
+    return sizeof(double) * (size_t)(NB * NQ + region(Np, Nf) + NB * rsep_per_column<N1>());
   }
 };
 
@@ -495,7 +532,7 @@ k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restric
   SSE_LOOP(idx, NB * Np) bufP[idx] = (idx < Ev * Np) ? __ldcg(u + k0 * Np + idx) : 0.0;
   __syncthreads();
   apply_V_t<DIM, N1, NB, 1>(vtab(T), bufP, bufQ, tmp);
-  apply_R_t<NQ, NB, 1, Nf, N1>(T, bufQ, bufF);
+  apply_R_t<NQ, NB, 1, Nf, N1>(T, bufQ, bufF, tmp + NodalBatchCfg<DIM, N1, NB>::region(Np, Nf));
   SSE_LOOP(idx, Ev * NQ) u_q[k0 * NQ + idx] = bufQ[idx];
   SSE_LOOP(idx, Ev * Nf) u_f[k0 * Nf + idx] = bufF[idx];
 }
@@ -577,6 +614,25 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   const int e = active ? tid / NQ : 0;
   const int i = active ? tid % NQ : 0;
 
+  // L2 prefetch of the inputs of the CTA that will run in this slot one wave later (CTAs are
+  // scheduled in blockIdx order, pf_dist = SMs x resident CTAs x EL elements ahead): its
+  // prologue then waits for L2 instead of DRAM.
+  if (G.pf_dist > 0) {
+    const long long kp = k0 + G.pf_dist;
+    if (kp + EL <= G.N_e) {
+      auto pf = [&](const void* base, int bytes) {
+        for (int o = tid * 128; o < bytes; o += 128 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)base + o));
+      };
+      pf(u_q + kp * NC * NQ, EL * NC * NQ * 8);
+      pf(G.L_q + kp * DD * NQ, EL * DD * NQ * 8);
+      pf(G.nJf + kp * NF * DIM, EL * NF * DIM * 8);
+      pf(u_f + kp * NC * NF, EL * NC * NF * 8);
+      pf(G.J_f + kp * NF, EL * NF * 8);
+      pf(G.toff + kp * NF, EL * NF * 4);
+      pf(G.J_q + kp * NQ, EL * NQ * 8);
+    }
+  }
   double si[2 * NS2], Li[DD], r[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) r[c] = 0.0;
@@ -939,6 +995,20 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     }
   }
   __syncthreads();
+  // separable collapsed-face rows of R (see apply_R_t): shared a3-contraction of φ, kept in sR
+  // (free until phase 2)
+  const int ng = T.R_ng;
+  if (ng > 0) {
+    SSE_LOOP(idx, NB * ng * N1) {
+      const int a2 = idx % N1, g = (idx / N1) % ng, b = idx / (N1 * ng);
+      const double* s0 = sPhi + b * NQ + __ldg(T.R_gstart + g) + a2 * N1;
+      double acc = 0.0;
+#pragma unroll
+      for (int a3 = 0; a3 < N1; ++a3) acc = fma(T.R_r3[a3], s0[a3], acc);
+      sR[idx] = acc;
+    }
+    __syncthreads();
+  }
   // ---- phase 1: facet nodes: f_f = B J_f (f* − ½ (a·n) (R φ))
   for (int idx = tid; idx < NB * NF; idx += 128) {
     const int j = idx % NF, b = idx / NF;
@@ -963,6 +1033,10 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     if (cnt == N1) {
 #pragma unroll
       for (int q = 0; q < N1; ++q) rphi = fma(__ldg(T.R_v + rb + q), ph[q * stride], rphi);
+    } else if (ng > 0 && cnt == N1 * N1 && stride == 1) {
+      const double* t0 = sR + (b * ng + __ldg(T.R_grp + j)) * N1;
+#pragma unroll
+      for (int a2 = 0; a2 < N1; ++a2) rphi = fma(__ldg(T.R_E + j * N1 + a2), t0[a2], rphi);
     } else if (cnt == N1 * N1 && stride == 1) {
       double part[N1];
 #pragma unroll

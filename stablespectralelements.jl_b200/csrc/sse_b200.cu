@@ -235,6 +235,12 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
   CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
+  {
+    static int sms = 0;
+    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const char* e = getenv("SSE_B200_PREFETCH");
+    h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_NODAL_MINB * EL;
+  }
   k_nodal_tensor<DIM, N1, LAW, true><<<grid, 128, smem, h->stream>>>(
       h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
   h->launches++;
@@ -250,6 +256,12 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   CU(cudaFuncSetAttribute(k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
+  {
+    static int sms = 0;
+    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const char* e = getenv("SSE_B200_PREFETCH");
+    h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_FD_MINB * Cf::EL;
+  }
   k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, 128, smem, h->stream>>>(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
@@ -521,6 +533,51 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     }
     h->r_ap = ap;
     if (ap && dev_upload_vec(h, desc, &T.R_desc)) return -1;
+    // separable rows: N1^2 contiguous entries that factor as E_j[a2] * r3[a3] with a common r3
+    T.R_ng = 0;
+    const int n1r = ops->n1d;
+    if (ap && n1r >= 2 && n1r <= 8) {
+      std::vector<int> blocks, gstart, grp(Nf, 0);
+      for (int j = 0; j < Nf; ++j) {
+        const int cnt = R.rp[j + 1] - R.rp[j];
+        if (cnt == n1r * n1r && cnt > n1r && ((desc[j] >> 10) & 1023) == 1) blocks.push_back(j);
+      }
+      bool sep = !blocks.empty();
+      std::vector<double> r3(8, 0.0), RE((size_t)Nf * n1r, 0.0);
+      if (sep) {
+        const double* M0 = R.v.data() + R.rp[blocks[0]];
+        int piv = 0;
+        for (int q = 1; q < n1r * n1r; ++q)
+          if (std::fabs(M0[q]) > std::fabs(M0[piv])) piv = q;
+        const int a2p = piv / n1r, a3p = piv % n1r;
+        for (int a3 = 0; a3 < n1r; ++a3) r3[a3] = M0[a2p * n1r + a3] / M0[piv];
+        for (int j : blocks) {
+          const double* M = R.v.data() + R.rp[j];
+          double mx = 0.0;
+          for (int q = 0; q < n1r * n1r; ++q) mx = std::max(mx, std::fabs(M[q]));
+          for (int a2 = 0; a2 < n1r; ++a2) {
+            const double e = M[a2 * n1r + a3p];
+            RE[(size_t)j * n1r + a2] = e;
+            for (int a3 = 0; a3 < n1r; ++a3)
+              if (std::fabs(M[a2 * n1r + a3] - e * r3[a3]) > 1e-14 * mx) sep = false;
+          }
+          const int st = desc[j] & 1023;
+          int g = -1;
+          for (size_t q = 0; q < gstart.size(); ++q)
+            if (gstart[q] == st) g = (int)q;
+          if (g < 0) { g = (int)gstart.size(); gstart.push_back(st); }
+          grp[j] = g;
+        }
+        if ((int)gstart.size() > n1r) sep = false;
+      }
+      if (sep && !getenv("SSE_B200_NO_RSEP")) {
+        T.R_ng = (int)gstart.size();
+        for (int a3 = 0; a3 < 8; ++a3) T.R_r3[a3] = r3[a3];
+        if (dev_upload_vec(h, gstart, &T.R_gstart) || dev_upload_vec(h, grp, &T.R_grp) ||
+            dev_upload_vec(h, RE, &T.R_E))
+          return -1;
+      }
+    }
   }
   if (dev_upload_vec(h, R.rp, &T.R_rp) || dev_upload_vec(h, R.ci, &T.R_ci) ||
       dev_upload_vec(h, R.v, &T.R_v) || dev_upload_vec(h, Rslot, &T.R_slot) ||
@@ -863,7 +920,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   }
   auto smem_a_fast = [&](int E) {
     // upper bound of NodalCfg::bytes (the launch computes the exact figure)
-    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 3 * (size_t)Nc * Nq + (size_t)Nc * Nf);
+    return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 4 * (size_t)Nc * Nq + (size_t)Nc * Nf);
   };
   auto smem_b_fast = [&](int E) {
     const size_t H = (size_t)h->n1 / 2;
