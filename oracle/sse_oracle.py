@@ -11,12 +11,15 @@ holds no residual-level golden vectors.  What pins this oracle instead (tests/te
     (/root/reference/test/runtests.jl:34-143) for the cases whose meshes are unambiguous without
     StartUpDG (1-D advection-diffusion ModalMulti/BR1/PhysicalOperator; 1-D Euler Gauss
     collocation flux differencing with entropy projection and facet correction; 2-D Euler
-    vortex ModalTensor Tri flux differencing with Lax-Friedrichs), reproduced by integrating
-    this oracle with the same CK54 scheme and time step;
+    vortex ModalTensor Tri flux differencing with Lax-Friedrichs; 3-D Euler NodalTensor Hex
+    flux differencing with the EC interface flux and conservative-curl metrics), reproduced by
+    integrating this oracle with the same scheme (CK54 / DP8) and time step;
   * the reference's conservation / energy / entropy invariants (Analysis/conservation.jl:145-190).
 For the north-star configuration itself (flux differencing on tetrahedra) the reference has no
 test of any kind: at that boundary parity is "unpinned by golden vectors" and rests on the
-shared code path with the pinned 1-D/2-D cases plus the invariants.
+shared code path with the pinned cases -- the 3-D Euler physics (two-point flux, entropy maps,
+3-D conservative-curl metrics) through the Hex case, the collapsed-coordinate modal operators,
+entropy projection and facet correction through the 2-D Tri case -- plus the invariants.
 
 Array convention: a Julia array A[i1, ..., k] is the C-contiguous NumPy array A[k, ..., i1]
 (identical bytes).  ``u``/``dudt`` are (N_e, N_c, N_p).
@@ -524,6 +527,30 @@ def ck54_integrate(rhs, u0, tspan, dt, callback=None):
     return u
 
 
+def dp8_integrate(rhs, u0, tspan, n_steps):
+    """Dormand-Prince 8(5,3) with a fixed step -- OrdinaryDiffEq's ``DP8(adaptive=false)`` as
+    used by test/euler_3d.jl:44-51.  OrdinaryDiffEq is not vendored; DP8 there is Hairer's DOP853
+    tableau, whose published coefficients ship with SciPy (scipy.integrate DOP853): 12 stages,
+    u_{n+1} = u_n + h Σ b_s k_s."""
+    from scipy.integrate._ivp import dop853_coefficients as dc
+    A, B, C = dc.A[:12, :12], dc.B, dc.C[:12]
+    u = u0.copy()
+    h = (tspan[1] - tspan[0]) / n_steps
+    for n in range(n_steps):
+        t = tspan[0] + n * h
+        K = []
+        for s in range(12):
+            us = u.copy()
+            for j in range(s):
+                if A[s, j] != 0.0:
+                    us += (h * A[s, j]) * K[j]
+            K.append(rhs(us, t + C[s] * h))
+        for s in range(12):
+            if B[s] != 0.0:
+                u = u + (h * B[s]) * K[s]
+    return u
+
+
 # ========================================================================== functionals
 def conservation_residual(prob, dudt):
     """Analysis/conservation.jl:145-152: Σ_k 1ᵀ W J_k V dudt_k per variable."""
@@ -560,6 +587,22 @@ def l2_error(prob, u, exact_q):
     u_q = np.einsum("qp,kep->kqe", prob["V"], u)
     WJ = prob["W"][None, :] * prob["J_q"]
     return np.sqrt(np.einsum("kq,kqe->e", WJ, (exact_q - u_q) ** 2))
+
+
+def l2_error_quadrature(prob, u, exact, xyzq, t, volq_to_err, w_err):
+    """Analysis/error.jl:13-91 with a separate error quadrature: ``volq_to_err`` (N_err, N_q) =
+    V_modes_to_errq P_volq_to_modes interpolates volume-node values (coordinates, Jacobian and,
+    through V, the solution) to the error-quadrature nodes with weights ``w_err``.
+    ``xyzq``: d arrays (N_e, N_q); ``exact(x..., t)`` -> tuple of N_c arrays."""
+    V_err = volq_to_err @ prob["V"]
+    err = np.zeros(u.shape[1])
+    for k in range(u.shape[0]):
+        x_err = [volq_to_err @ x[k] for x in xyzq]
+        ue = np.stack(exact(*x_err, t), axis=-1)
+        ua = np.einsum("qp,ep->qe", V_err, u[k])
+        wj = w_err * (volq_to_err @ prob["J_q"][k])
+        err += np.einsum("q,qe->e", wj, (ue - ua) ** 2)
+    return np.sqrt(err)
 
 
 def project_initial_data(prob, u_q):

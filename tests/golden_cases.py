@@ -12,7 +12,7 @@ from sse_b200.conservation_laws import (CentralNumericalFlux, EntropyConservativ
                                         LinearAdvectionDiffusionEquation,
                                         LinearAdvectionEquation, BR1)
 from sse_b200.geometric_factors import ChanWilcoxMetrics, make_spatial_discretization
-from sse_b200.grid_functions import (InitialDataCosine, InitialDataGassner, InitialDataSine,
+from sse_b200.grid_functions import (EulerPeriodicTest, InitialDataCosine, InitialDataGassner, InitialDataSine,
                                      IsentropicVortex, evaluate)
 from sse_b200.mesh import ChanWarping, uniform_periodic_mesh, warp_mesh
 from sse_b200.reference_approximation import (Hex, LGQuadrature, Line, ModalMulti, ModalTensor,
@@ -141,3 +141,24 @@ def advection_3d_tet(lazy=True):
     def exact(x, y, z, t):
         return (np.cos(2 * math.pi * x) * np.cos(2 * math.pi * y) * np.cos(2 * math.pi * z),)
     return solver, project_function(ic, sd), 1.0, dt, exact, [0.1876141674772107]
+
+
+def euler_3d_hex(lazy=True):
+    """runtests.jl:131-144, test/euler_3d.jl: 3-D Euler, NodalTensor(4) Hex, M = 2, ChanWarping,
+    conservative-curl metrics, flux differencing with the EC interface flux; integrated with
+    DP8, N_t = 25 M (p+1) fixed steps (the tuple's dt slot holds N_t)."""
+    g, L, M, p = 1.4, 2.0, 2, 4
+    law = EulerEquations(3, g)
+    ra = make_reference_approximation(NodalTensor(p), Hex(), mapping_degree=p)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, L),) * 3, (M,) * 3), ra,
+                     ChanWarping(1.0 / 16.0, (L, L, L)))
+    sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
+    form = FluxDifferencingForm(inviscid_numerical_flux=EntropyConservativeNumericalFlux())
+    solver = Solver(law, sd, form, ReferenceOperator(), lazy=lazy)
+    ic = EulerPeriodicTest(3, g, 0.2, L)
+
+    def exact(x, y, z, t):
+        return tuple(evaluate(ic, (x, y, z), t))
+    return solver, project_function(ic, sd), L, 25 * M * (p + 1), exact, \
+        [0.18342164491797003, 0.1834216449179776, 0.18342164491796725, 0.18342164491796784,
+         0.2751324673769553]
