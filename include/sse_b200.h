@@ -141,13 +141,27 @@ int sse_rk_stage(sse_handle* h, double a, double b, double dt);
 int sse_rk_step_ck54(sse_handle* h, double dt);   /* Carpenter-Kennedy (5,4), 5 fused stages */
 
 /* Halo of facet traces for element-sharded runs.  send_idx: n_send linear indices (j + N_f*k)
- * of local trace nodes to pack; the packed buffer holds N_c doubles per index, variable-major
- * ([c][n]).  Received values are unpacked into halo slots [0, N_halo). */
+ * of local trace nodes to pack; the packed buffer holds N_c doubles per index, node-major
+ * ([n][c]).  Received values are unpacked into halo slots [0, N_halo). */
 int sse_halo_setup(sse_handle* h, const int64_t* send_idx, int64_t n_send);
 int sse_halo_buffers(sse_handle* h, double** send_dev, double** recv_dev, int64_t* n_send,
                      int64_t* n_recv);
 int sse_halo_pack(sse_handle* h);      /* traces -> send buffer (after sse_nodal_values)     */
 int sse_halo_unpack(sse_handle* h);    /* recv buffer -> halo trace slots                     */
+
+/* Second-order (BR1) equations on element shards.  The reference runs three element loops with a
+ * barrier after each (Solvers/Solvers.jl:520-570): nodal_values!, auxiliary_variable!
+ * (standard_form_second_order.jl:3-40) and time_derivative! (:42-75); the last one reads the
+ * neighbour's auxiliary-variable trace q_f, so a sharded run exchanges a second halo in between:
+ *   sse_nodal_values -> pack/exchange/unpack u_f -> sse_auxiliary_variable_range (all elements)
+ *   -> sse_halo_pack_aux / exchange / sse_halo_unpack_aux -> sse_time_derivative_only_range.
+ * The aux halo uses the same send list and buffers, dim * N_c doubles per node ([node][m][c]).
+ * sse_time_derivative(_range) keeps running both loops back to back (single-GPU use). */
+int sse_auxiliary_variable_range(sse_handle* h, int64_t k_begin, int64_t k_end);
+int sse_time_derivative_only_range(sse_handle* h, double* dudt_dev, int64_t k_begin,
+                                   int64_t k_end);
+int sse_halo_pack_aux(sse_handle* h);
+int sse_halo_unpack_aux(sse_handle* h);
 
 /* Streams / timing / introspection. */
 /* Host-buffer building blocks for element-sharded runs: chunked H2D of u overlapped with loop A

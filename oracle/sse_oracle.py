@@ -460,28 +460,42 @@ def residual_standard_physical_first_order(prob, u):
     return np.einsum("kmpq,kqem->kep", VOL, f_q) + np.einsum("kpf,kfe->kep", FAC, f_f)
 
 
-def residual_standard_physical_second_order(prob, u):
-    """Solvers.jl:520-570 with standard_form_second_order.jl:3-75 (BR1)."""
-    law, form = prob["law"], prob["form"]
-    d = prob["d"]
+def second_order_auxiliary_variable(prob, u_q, u_f, u_out):
+    """Loop A2, ``auxiliary_variable!`` (standard_form_second_order.jl:3-40): BR1 gradient
+    q = -(VOL u_q + FAC u* n), u* n = ½(u⁻+u⁺) n (linear_advection_diffusion.jl:77-89);
+    returns q_q (N_e,N_q,N_c,d) and q_f (N_e,N_f,N_c,d)."""
     V, R = prob["V"], prob["R"]
     VOL, FAC = physical_operators(prob)
     n_f = _n_f_physical(prob)
-    mapP = prob["mapP"]
-    u_q = np.einsum("qp,kep->kqe", V, u)
-    u_f = np.einsum("fq,kqe->kfe", R, u_q)
-    u_out = _gather_exterior(u_f, mapP)
-    # auxiliary variable: u* n = ½(u⁻+u⁺) n  (linear_advection_diffusion.jl:77-89)
     u_n = 0.5 * (u_f + u_out)[..., None] * n_f[:, :, None, :]          # (N_e,N_f,N_c,d)
     q = -(np.einsum("kmpq,kqe->kepm", VOL, u_q) + np.einsum("kpf,kfem->kepm", FAC, u_n))
     q_q = np.einsum("qp,kepm->kqem", V, q)
     q_f = np.einsum("fq,kqem->kfem", R, q_q)
-    q_out = np.stack([_gather_exterior(q_f[..., m], mapP) for m in range(d)], axis=-1)
+    return q_q, q_f
+
+
+def second_order_time_derivative(prob, u_q, u_f, u_out, q_q, q_f, q_out):
+    """Loop B, ``time_derivative!`` (standard_form_second_order.jl:42-75)."""
+    law, form = prob["law"], prob["form"]
+    VOL, FAC = physical_operators(prob)
+    n_f = _n_f_physical(prob)
     f_q = physical_flux(law, u_q, q_q)
     f_f = numerical_flux(law, form["inviscid"], u_f, u_out, n_f, "conservative")
     # BR1 viscous flux: f* += Σ_m b (−½(q⁻+q⁺))_m n_m  (linear_advection_diffusion.jl:91-105)
     f_f = f_f + np.einsum("kfem,kfm->kfe", law["b"] * (-0.5) * (q_f + q_out), n_f)
     return np.einsum("kmpq,kqem->kep", VOL, f_q) + np.einsum("kpf,kfe->kep", FAC, f_f)
+
+
+def residual_standard_physical_second_order(prob, u):
+    """Solvers.jl:520-570 with standard_form_second_order.jl:3-75 (BR1): three element loops."""
+    d = prob["d"]
+    mapP = prob["mapP"]
+    u_q = np.einsum("qp,kep->kqe", prob["V"], u)
+    u_f = np.einsum("fq,kqe->kfe", prob["R"], u_q)
+    u_out = _gather_exterior(u_f, mapP)
+    q_q, q_f = second_order_auxiliary_variable(prob, u_q, u_f, u_out)
+    q_out = np.stack([_gather_exterior(q_f[..., m], mapP) for m in range(d)], axis=-1)
+    return second_order_time_derivative(prob, u_q, u_f, u_out, q_q, q_f, q_out)
 
 
 def semi_discrete_residual(prob, u, t=0.0):

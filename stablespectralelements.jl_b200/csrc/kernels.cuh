@@ -862,6 +862,30 @@ __global__ void k_halo_unpack(double* __restrict__ u_f, const double* __restrict
   }
 }
 
+// the same for the BR1 auxiliary-variable traces q_f [k][m][c][j]: DIM * NC doubles per node,
+// ordered [m][c].  off[s] = k * NC * Nf + j is the u_f offset of the node (sse_halo_setup).
+__global__ void k_halo_pack_aux(const double* __restrict__ q_f, const int* __restrict__ off, int n,
+                                int NC, int D, int Nf, double* __restrict__ send) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) {
+    const long long k = off[s] / (NC * Nf);
+    const int j = off[s] % (NC * Nf);
+    for (int mc = 0; mc < D * NC; ++mc)
+      send[(long long)s * D * NC + mc] = q_f[(k * D * NC + mc) * Nf + j];
+  }
+}
+
+__global__ void k_halo_unpack_aux(double* __restrict__ q_f, const double* __restrict__ recv, int n,
+                                  int NC, int D, int Nf, long long N_e) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < n) {
+    long long kk = N_e + h / Nf;
+    int j = h % Nf;
+    for (int mc = 0; mc < D * NC; ++mc)
+      q_f[(kk * D * NC + mc) * Nf + j] = recv[(long long)h * D * NC + mc];
+  }
+}
+
 __global__ void k_axpy_rk(double* __restrict__ u, double* __restrict__ k, const double* r,
                           double a, double b, double dt, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -75,6 +75,7 @@ struct sse_handle {
   int64_t n_send = 0;
   // launch configuration
   int second_order = 0, proj = 0, law_t = 0;
+  int b_stages = 3;   // second order: bit 0 = auxiliary_variable! (A2), bit 1 = time_derivative!
   int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
   size_t smem_a = 0, smem_b = 0;
   // compile-time specialised tensor-product path
@@ -173,11 +174,15 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
   if (h->cfg.strategy == SSE_PHYSICAL_OPERATOR) {
     CU(cudaFuncSetAttribute(k_physical<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)h->smem_b));
-    if (h->second_order) {
+    if (h->second_order && (h->b_stages & 1)) {
       RK none{};
       k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
           h->T, h->G, h->P, none, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 0, 1);
       h->launches++;
+      if (!(h->b_stages & 2)) {
+        CU(cudaGetLastError());
+        return 0;
+      }
     }
     k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
         h->T, h->G, h->P, rk, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 1,
@@ -846,13 +851,16 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       dev_upload<double>(h, nullptr, (size_t)Nf * Nc * (Ne + h->halo_elems), &h->u_f))
     return -1;
   if (h->second_order) {
-    if (cfg->N_halo) return fail("halo exchange is not implemented for second-order equations");
+    // q_f carries the same halo pseudo-elements as u_f (BR1 needs the neighbour's q trace)
     if (dev_upload<double>(h, nullptr, (size_t)Nq * Nc * d * Ne, &h->q_q) ||
-        dev_upload<double>(h, nullptr, (size_t)Nf * Nc * d * Ne, &h->q_f))
+        dev_upload<double>(h, nullptr, (size_t)Nf * Nc * d * (Ne + h->halo_elems), &h->q_f))
       return -1;
   }
   if (cfg->N_halo) {
-    if (dev_upload<double>(h, nullptr, (size_t)cfg->N_halo * Nc, &h->recv_buf)) return -1;
+    // second order: the buffers also carry q_f (d * N_c doubles per node)
+    if (dev_upload<double>(h, nullptr, (size_t)cfg->N_halo * Nc * (h->second_order ? d : 1),
+                           &h->recv_buf))
+      return -1;
   }
 
   // ---- projection mode of loop A (flux_differencing_form.jl:171-292)
@@ -1145,7 +1153,9 @@ int sse_halo_setup(sse_handle* h, const int64_t* send_idx, int64_t n_send) {
     off[s] = (int)((g / Nf) * Nc * Nf + g % Nf);
   }
   if (dev_upload(h, off.data(), off.size(), &h->send_off)) return -1;
-  if (dev_upload<double>(h, nullptr, (size_t)n_send * Nc, &h->send_buf)) return -1;
+  if (dev_upload<double>(h, nullptr, (size_t)n_send * Nc * (h->second_order ? h->cfg.dim : 1),
+                         &h->send_buf))
+    return -1;
   h->n_send = n_send;
   return 0;
 }
@@ -1184,7 +1194,8 @@ int sse_halo_unpack(sse_handle* h) {
   return 0;
 }
 
-int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end) {
+static int time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end,
+                                 int stages) {
   if (!h) return fail("null handle");
   if (k_begin < 0 || k_end > h->cfg.N_e || k_begin > k_end) return fail("bad element range");
   if (k_begin == k_end) return 0;
@@ -1192,10 +1203,53 @@ int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, 
   RK rk{};
   h->G.k_begin = k_begin;
   h->G.N_e = k_end;
+  h->b_stages = stages;
   int rc = run_b(h, dudt_dev ? dudt_dev : h->dudt, rk);
+  h->b_stages = 3;
   h->G.k_begin = 0;
   h->G.N_e = h->cfg.N_e;
   return rc;
+}
+
+int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end) {
+  return time_derivative_range(h, dudt_dev, k_begin, k_end, 3);
+}
+
+int sse_auxiliary_variable_range(sse_handle* h, int64_t k_begin, int64_t k_end) {
+  if (!h) return fail("null handle");
+  if (!h->second_order) return 0;   // first-order equations have no auxiliary variable
+  return time_derivative_range(h, nullptr, k_begin, k_end, 1);
+}
+
+int sse_time_derivative_only_range(sse_handle* h, double* dudt_dev, int64_t k_begin,
+                                   int64_t k_end) {
+  return time_derivative_range(h, dudt_dev, k_begin, k_end, 2);
+}
+
+int sse_halo_pack_aux(sse_handle* h) {
+  if (!h) return fail("null handle");
+  if (!h->second_order) return fail("sse_halo_pack_aux: not a second-order equation");
+  if (h->n_send == 0) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  int n = (int)h->n_send;
+  k_halo_pack_aux<<<(n + 255) / 256, 256, 0, h->stream>>>(h->q_f, h->send_off, n, h->cfg.N_c,
+                                                          h->cfg.dim, h->cfg.N_f, h->send_buf);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sse_halo_unpack_aux(sse_handle* h) {
+  if (!h) return fail("null handle");
+  if (!h->second_order) return fail("sse_halo_unpack_aux: not a second-order equation");
+  if (h->cfg.N_halo == 0) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  int n = (int)h->cfg.N_halo;
+  k_halo_unpack_aux<<<(n + 255) / 256, 256, 0, h->stream>>>(h->q_f, h->recv_buf, n, h->cfg.N_c,
+                                                            h->cfg.dim, h->cfg.N_f, h->cfg.N_e);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int sse_set_stream(sse_handle* h, void* stream) {

@@ -71,7 +71,9 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_measure_fp64_peak", "sse_time_derivative_range", "sse_set_stream",
            "sse_upload_state", "sse_download_dudt", "sse_upload_and_nodal_values",
            "sse_download_dudt_range", "sse_sync_copies", "sse_functional",
-           "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host"]
+           "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host",
+           "sse_auxiliary_variable_range", "sse_time_derivative_only_range",
+           "sse_halo_pack_aux", "sse_halo_unpack_aux"]
 
 
 def load_library(path: Optional[str] = None):
@@ -122,6 +124,10 @@ def load_library(path: Optional[str] = None):
     lib.sse_geometry_build.argtypes = [C.POINTER(SseMapping), C.POINTER(SseGeometry)]
     lib.sse_geometry_free.argtypes = [C.POINTER(SseGeometry)]
     lib.sse_copy_to_host.argtypes = [vp, vp, C.c_int64]
+    lib.sse_auxiliary_variable_range.argtypes = [vp, C.c_int64, C.c_int64]
+    lib.sse_time_derivative_only_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    lib.sse_halo_pack_aux.argtypes = [vp]
+    lib.sse_halo_unpack_aux.argtypes = [vp]
     if path is None:
         _LIB = lib
     return lib
@@ -457,3 +463,20 @@ class DeviceResidual:
 
     def halo_unpack(self):
         self._check(self.lib.sse_halo_unpack(self.h), "sse_halo_unpack")
+
+    # second-order (BR1) equations on shards: the two loops of sse_time_derivative separately,
+    # and the halo of the auxiliary-variable traces q_f exchanged in between
+    def auxiliary_variable_range(self, k_begin: int, k_end: int):
+        self._check(self.lib.sse_auxiliary_variable_range(self.h, k_begin, k_end),
+                    "sse_auxiliary_variable_range")
+
+    def time_derivative_only_range(self, k_begin: int, k_end: int, dudt_ptr: int = 0):
+        self._check(self.lib.sse_time_derivative_only_range(self.h, dudt_ptr or None, k_begin,
+                                                            k_end),
+                    "sse_time_derivative_only_range")
+
+    def halo_pack_aux(self):
+        self._check(self.lib.sse_halo_pack_aux(self.h), "sse_halo_pack_aux")
+
+    def halo_unpack_aux(self):
+        self._check(self.lib.sse_halo_unpack_aux(self.h), "sse_halo_unpack_aux")

@@ -10,6 +10,10 @@ elements needs exactly one neighbour exchange of trace values between loop A and
     loop B on interior elements (overlaps the transfer)    ->  unpack halo  ->  loop B on the
     boundary elements.
 
+Second-order (BR1) equations read the neighbour's auxiliary-variable trace ``q_f`` as well
+(standard_form_second_order.jl:63-64), so they exchange twice: u_f before ``auxiliary_variable!``
+and q_f before ``time_derivative!`` (``DistributedResidual._flow``).
+
 ``partition`` is pure NumPy (tested on CPU with gloo, tests/test_distributed_cpu.py).
 """
 from __future__ import annotations
@@ -118,7 +122,8 @@ class DistributedResidual:
         from .device import DeviceResidual
         self.solver, self.rank, self.world = solver, rank, world
         sd = solver.spatial_discretization
-        N_f = sd.reference_approximation.N_f
+        self.dim = sd.reference_approximation.dim
+        self.second_order = solver.law_desc["kind"] in ("advection_diffusion", "viscous_burgers")
         if world == 1:
             self.part = None
             self.elements = np.arange(sd.N_e)
@@ -139,10 +144,11 @@ class DistributedResidual:
                                           n_halo=self.part.n_halo, elements=self.elements)
             self.dev.halo_setup(self.part.send_idx)
             s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
-            N_c = self.dev.N_c
+            # doubles per trace node: N_c for u_f, dim * N_c for the BR1 auxiliary traces q_f
+            width = self.dev.N_c * (self.dim if self.second_order else 1)
             dv = torch.device("cuda", device)
-            self.send_t = torch.as_tensor(_DevBuf(s_ptr, n_s * N_c), device=dv)
-            self.recv_t = torch.as_tensor(_DevBuf(r_ptr, n_r * N_c), device=dv)
+            self.send_t = torch.as_tensor(_DevBuf(s_ptr, n_s * width), device=dv)
+            self.recv_t = torch.as_tensor(_DevBuf(r_ptr, n_r * width), device=dv)
             # run the library on torch's current stream so NCCL ordering is stream-ordered
             self.dev.set_stream(torch.cuda.current_stream(dv).cuda_stream)
             self._ops = None
@@ -150,44 +156,87 @@ class DistributedResidual:
         self.n_local_state = int(np.prod(self.local_shape))
 
     # ------------------------------------------------------------------ plumbing
-    def _p2p_ops(self):
-        import torch.distributed as dist
-        ops, so, ro = [], 0, 0
-        N_c = self.dev.N_c
+    def halo_segments(self, width: int):
+        """peer -> (send slice, recv slice) of the packed buffers, ``width`` doubles per node."""
+        seg, so, ro = {}, 0, 0
         for peer in sorted(set(self.part.send_counts) | set(self.part.recv_counts)):
-            ns = self.part.send_counts.get(peer, 0) * N_c
-            nr = self.part.recv_counts.get(peer, 0) * N_c
-            if nr:
-                ops.append(dist.P2POp(dist.irecv, self.recv_t[ro:ro + nr], peer))
-            if ns:
-                ops.append(dist.P2POp(dist.isend, self.send_t[so:so + ns], peer))
+            ns = self.part.send_counts.get(peer, 0) * width
+            nr = self.part.recv_counts.get(peer, 0) * width
+            seg[peer] = (slice(so, so + ns), slice(ro, ro + nr))
             so += ns
             ro += nr
+        return seg
+
+    def _p2p_ops(self, width: Optional[int] = None):
+        """isend/irecv pairs of one halo exchange, ``width`` doubles per trace node."""
+        import torch.distributed as dist
+        ops = []
+        width = self.dev.N_c if width is None else width
+        for peer, (snd, rcv) in self.halo_segments(width).items():
+            if rcv.stop > rcv.start:
+                ops.append(dist.P2POp(dist.irecv, self.recv_t[rcv], peer))
+            if snd.stop > snd.start:
+                ops.append(dist.P2POp(dist.isend, self.send_t[snd], peer))
         return ops
 
-    def _exchange_and_time_derivative(self, dudt_host=None):
-        """Halo exchange + loop B.  With ``dudt_host`` the result is copied back range by range
-        while later ranges still compute (the interior is cut into a few pieces for that)."""
-        import torch.distributed as dist
+    def _flow(self, dudt_host=None):
+        """Everything after loop A, as a generator: it yields the number of doubles per trace
+        node each time a halo exchange of the packed send buffer has to be STARTED and is sent
+        back a ``wait()`` callable, which it calls right before it needs the received values --
+        the element ranges that read no halo value run in between and overlap the transfer.
+        (The caller owns the transport: NCCL in production, device copies between two shards on
+        one GPU in tests/test_gpu_sharded_emulation.py.)
+
+        First order: loop B.  Second order (BR1; Solvers.jl:520-570): loop A2
+        (``auxiliary_variable!``) needs the neighbour's u_f, loop B (``time_derivative!``) the
+        neighbour's q_f -- two exchanges.  With ``dudt_host`` the result is copied back range by
+        range while later ranges still compute (the interior is cut into a few pieces for that).
+        """
         d = self.dev
-        d.halo_pack()
-        works = dist.batch_isend_irecv(self._p2p_ops())
         k_lo, k_hi = self.part.interior
-        if k_hi > k_lo:                                    # overlaps the NVLink transfer
-            npieces = 6 if (dudt_host is not None and k_hi - k_lo >= 6 * 4096) else 1
-            cuts = [k_lo + ((k_hi - k_lo) * q) // npieces for q in range(npieces + 1)]
-            for a, b in zip(cuts[:-1], cuts[1:]):
-                d.time_derivative_range(a, b)
+        boundary = [(a, b) for a, b in ((0, k_lo), (max(k_hi, k_lo), d.N_e)) if b > a]
+        npieces = 6 if (dudt_host is not None and k_hi - k_lo >= 6 * 4096) else 1
+        cuts = [k_lo + ((k_hi - k_lo) * q) // npieces for q in range(npieces + 1)]
+        interior = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+        def loop_b(ranges, fn):
+            for a, b in ranges:
+                fn(a, b)
                 if dudt_host is not None:
                     d.download_dudt_range(dudt_host, a, b)
-        for w in works:
-            w.wait()
+
+        d.halo_pack()
+        wait = yield d.N_c
+        if not self.second_order:
+            loop_b(interior, d.time_derivative_range)          # overlaps the NVLink transfer
+            wait()
+            d.halo_unpack()
+            loop_b(boundary, d.time_derivative_range)
+            return
+        if k_hi > k_lo:
+            d.auxiliary_variable_range(k_lo, k_hi)
+        wait()
         d.halo_unpack()
-        for a, b in ((0, k_lo), (max(k_hi, k_lo), d.N_e)):
-            if b > a:
-                d.time_derivative_range(a, b)
-                if dudt_host is not None:
-                    d.download_dudt_range(dudt_host, a, b)
+        for a, b in boundary:
+            d.auxiliary_variable_range(a, b)
+        d.halo_pack_aux()
+        wait = yield d.N_c * self.dim
+        loop_b(interior, d.time_derivative_only_range)
+        wait()
+        d.halo_unpack_aux()
+        loop_b(boundary, d.time_derivative_only_range)
+
+    def _exchange_and_time_derivative(self, dudt_host=None):
+        """Halo exchange(s) over NCCL + the loops that follow loop A."""
+        import torch.distributed as dist
+        flow = self._flow(dudt_host)
+        try:
+            width = next(flow)
+            while True:
+                works = dist.batch_isend_irecv(self._p2p_ops(width))
+                width = flow.send(lambda works=works: [w.wait() for w in works])
+        except StopIteration:
+            pass
 
     def residual(self):
         """One residual of the device-resident state (dudt stays on the device)."""

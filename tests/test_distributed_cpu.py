@@ -26,6 +26,7 @@ def _restrict(prob, part):
     sl = slice(part.start, part.stop)
     loc = dict(prob)
     loc.pop("_SC", None)
+    loc.pop("_PHYS", None)
     for key in ("J_q", "Lambda_q", "J_f", "nJf"):
         loc[key] = prob[key][sl]
     loc["N_e"] = part.stop - part.start
@@ -74,6 +75,78 @@ def _worker(rank, world, port, builder, out):
             out.put([g.tolist() for g in gathered])
     finally:
         dist.destroy_process_group()
+
+
+def _exchange(part, send_rows, width):
+    """One halo exchange over gloo: rows of ``send_rows`` (n_send, width) go to the peers in the
+    partition's order; returns the (n_halo, width) halo rows."""
+    send = torch.from_numpy(np.ascontiguousarray(send_rows))
+    recv = torch.empty((part.n_halo, width), dtype=torch.float64)
+    ops, so, ro = [], 0, 0
+    for peer in sorted(set(part.send_counts) | set(part.recv_counts)):
+        ns, nr = part.send_counts.get(peer, 0), part.recv_counts.get(peer, 0)
+        if nr:
+            ops.append(dist.P2POp(dist.irecv, recv[ro:ro + nr], peer))
+        if ns:
+            ops.append(dist.P2POp(dist.isend, send[so:so + ns], peer))
+        so += ns
+        ro += nr
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return recv.numpy()
+
+
+def _worker_second_order(rank, world, port, builder, out):
+    """BR1: two exchanges -- u_f before auxiliary_variable!, q_f before time_derivative!."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        solver, u0 = getattr(cases, builder[0])(**builder[1])
+        u = cases.rough_state(solver, u0, seed=7)
+        prob = oracle_problem(solver)
+        part = partition(prob["mapP"], rank, world)
+        loc = _restrict(prob, part)
+        N_f, N_c, d = prob["N_f"], prob["N_c"], prob["d"]
+        gather = part.mapP_local.T.reshape(-1)
+        u_q = np.einsum("qp,kep->kqe", prob["V"], u[part.start:part.stop])
+        u_f = np.einsum("fq,kqe->kfe", prob["R"], u_q)
+        flat = u_f.reshape(-1, N_c)
+        halo = _exchange(part, flat[part.send_idx], N_c)
+        u_out = np.concatenate([flat, halo], axis=0)[gather].reshape(u_f.shape)
+        q_q, q_f = oc.second_order_auxiliary_variable(loc, u_q, u_f, u_out)
+        flat_q = q_f.reshape(-1, N_c * d)
+        halo_q = _exchange(part, flat_q[part.send_idx], N_c * d)
+        q_out = np.concatenate([flat_q, halo_q], axis=0)[gather].reshape(q_f.shape)
+        dudt = oc.second_order_time_derivative(loc, u_q, u_f, u_out, q_q, q_f, q_out)
+        ref = oc.semi_discrete_residual(prob, u)[part.start:part.stop]
+        res = torch.tensor([float(np.max(np.abs(dudt - ref))), 1.0, 0.0], dtype=torch.float64)
+        gathered = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, res)
+        if rank == 0:
+            out.put([g.tolist() for g in gathered])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,builder", [
+    (2, ("advection_diffusion_case", dict(d=1, p=4, M=6))),
+    (3, ("advection_diffusion_case", dict(d=2, p=3, M=4))),
+])
+def test_partitioned_second_order_residual_matches_global(world, builder):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_second_order, args=(r, world, port, builder, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for err, _, _ in res:
+        assert err < 1e-13, err
 
 
 @pytest.mark.parametrize("world,builder", [
