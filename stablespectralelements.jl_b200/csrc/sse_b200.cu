@@ -282,16 +282,6 @@ static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, KC, NB>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
-  {
-    static int sms = 0, resident = 0;   // per instantiation
-    if (!sms) {
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &resident, k_standard_tensor<DIM, N1, LAW, KC, NB>, 128, smem);
-    }
-    const char* e = getenv("SSE_B200_PREFETCH");
-    h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * resident * NB;
-  }
   k_standard_tensor<DIM, N1, LAW, KC, NB><<<grid, 128, smem, h->stream>>>(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;

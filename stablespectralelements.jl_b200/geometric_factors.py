@@ -21,7 +21,7 @@ import numpy as np
 
 from . import nodes as nd
 from . import polynomials as poly
-from .mesh import MeshData
+from .mesh import MeshData, run_chunks
 from .reference_approximation import (Hex, NoMapping, ReferenceApproximation, ReferenceMapping,
                                       RefElemData, Tet, Tri, reference_vertices, vandermonde)
 
@@ -91,8 +91,15 @@ def _facet_normals(Lambda_f, re: RefElemData):
     """nJf[m,i] = Σ_n Λ_f[i,n,m] nrstJ[n][i]; J_f = |nJf| (mesh.jl:273-281).
     Lambda_f: (N_e, N_f, d[l], d[m])."""
     nr = np.stack(re.nrstJ, axis=1)                      # (N_f, d)
-    nJf = np.einsum("kinm,in->kim", Lambda_f, nr)
-    J_f = np.sqrt(np.sum(nJf ** 2, axis=2))
+    N_e, N_f, d = Lambda_f.shape[:3]
+    nJf = np.empty((N_e, N_f, d))
+    J_f = np.empty((N_e, N_f))
+
+    def work(s, e):
+        nJf[s:e] = np.einsum("kinm,in->kim", Lambda_f[s:e], nr)
+        J_f[s:e] = np.sqrt(np.sum(nJf[s:e] ** 2, axis=2))
+
+    run_chunks(work, N_e, 8192)
     return nJf, J_f
 
 
@@ -133,47 +140,55 @@ def _curl_metrics_3d(x, y, z, Dr, Ds, Dt):
 
 
 def geometric_factors_curl(mesh: MeshData, re: RefElemData) -> GeometricFactors:
-    """mesh.jl:286-509 (2-D, Hex and Tet variants)."""
+    """mesh.jl:286-509 (2-D, Hex and Tet variants).  Elements are independent: chunks of them
+    are evaluated on a thread pool (mesh.run_chunks)."""
     d = re.dim
     elem = re.element_type
     N_e = mesh.N_e
     if d == 1:
         return geometric_factors_exact(mesh, re)
-    if d == 2:
-        x, y = mesh.xyz
-        Dr, Ds = re.Drst
-        xr, xs, yr, ys = Dr @ x, Ds @ x, Dr @ y, Ds @ y
-        J = -xs * yr + xr * ys
-        L = ((ys, -xs), (-yr, xr))               # L[l][m]: rxJ ryJ / sxJ syJ
-        Vq, Vf = re.Vq, re.Vf
-        J_q = (Vq @ J).T
-    elif isinstance(elem, Hex):
-        L, J = _curl_metrics_3d(*mesh.xyz, *re.Drst)
-        Vq, Vf = re.Vq, re.Vf
-        J_q = (Vq @ J).T
-    elif isinstance(elem, Tet):
+    tet = isinstance(elem, Tet)
+    if d == 3 and not tet and not isinstance(elem, Hex):
+        raise TypeError(elem)
+    if tet:
+        # the argument of the curl is a degree N+1 polynomial: evaluate it on a degree N+1
+        # nodal set, bring the (degree N) result back to the degree N nodes (mesh.jl:413-470)
         N = re.N
         r1, s1, t1 = nd.nodes_tet(N + 1)
         V1, Vr1, Vs1, Vt1 = poly.simplex_basis_3d(N + 1, r1, s1, t1, grad=True)
         N_to_Np1 = np.linalg.solve(re.VDM.T, vandermonde(elem, N, r1, s1, t1).T).T
         Np1_to_N = np.linalg.solve(V1.T, vandermonde(elem, N + 1, *re.rst).T).T
-        Vq = re.Vq @ Np1_to_N
-        Vf = re.Vf @ Np1_to_N
-        _, J = _curl_metrics_3d(*mesh.xyz, *re.Drst)
-        J_q = (re.Vq @ J).T
+        Vq, Vf = re.Vq @ Np1_to_N, re.Vf @ Np1_to_N
         D1 = tuple(np.linalg.solve(V1.T, g.T).T for g in (Vr1, Vs1, Vt1))
-        L, _ = _curl_metrics_3d(*(N_to_Np1 @ c for c in mesh.xyz), *D1)
     else:
-        raise TypeError(elem)
+        Vq, Vf = re.Vq, re.Vf
     N_q, N_f = Vq.shape[0], Vf.shape[0]
+    J_q = np.empty((N_e, re.Vq.shape[0]))
     Lambda_q = np.empty((N_e, d, d, N_q))         # [k, n, m, i]  (m = ξ index, n = x index)
     Lf = np.empty((N_e, N_f, d, d))               # [k, i, l, m]
-    for l in range(d):
-        for m in range(d):
-            Lambda_q[:, m, l, :] = (Vq @ L[l][m]).T
-            Lf[:, :, l, m] = (Vf @ L[l][m]).T
+
+    def work(s, e):
+        xyz = tuple(c[:, s:e] for c in mesh.xyz)
+        if d == 2:
+            x, y = xyz
+            Dr, Ds = re.Drst
+            xr, xs, yr, ys = Dr @ x, Ds @ x, Dr @ y, Ds @ y
+            J = -xs * yr + xr * ys
+            L = ((ys, -xs), (-yr, xr))               # L[l][m]: rxJ ryJ / sxJ syJ
+        elif tet:
+            _, J = _curl_metrics_3d(*xyz, *re.Drst)
+            L, _ = _curl_metrics_3d(*(N_to_Np1 @ c for c in xyz), *D1)
+        else:
+            L, J = _curl_metrics_3d(*xyz, *re.Drst)
+        J_q[s:e] = (re.Vq @ J).T
+        for l in range(d):
+            for m in range(d):
+                Lambda_q[s:e, m, l, :] = (Vq @ L[l][m]).T
+                Lf[s:e, :, l, m] = (Vf @ L[l][m]).T
+
+    run_chunks(work, N_e, 8192)
     nJf, J_f = _facet_normals(Lf, re)
-    return GeometricFactors(np.ascontiguousarray(J_q), Lambda_q, J_f, nJf, _n_ref(re))
+    return GeometricFactors(J_q, Lambda_q, J_f, nJf, _n_ref(re))
 
 
 class DeviceGeometricFactors:

@@ -24,6 +24,23 @@ from .reference_approximation import (Hex, Line, Quad, ReferenceApproximation, R
                                       Tet, Tri)
 
 
+def run_chunks(work, n: int, chunk: int):
+    """``work(start, stop)`` over [0, n) in chunks on a thread pool.  The host-side setup is
+    element-wise NumPy on large arrays, which releases the GIL; SSE_B200_SETUP_THREADS overrides
+    the thread count (1 = serial)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    spans = [(s, min(s + chunk, n)) for s in range(0, n, chunk)]
+    nthr = int(os.environ.get("SSE_B200_SETUP_THREADS", "0")) or min(16, os.cpu_count() or 1)
+    if nthr <= 1 or len(spans) <= 1:
+        for s, e in spans:
+            work(s, e)
+        return
+    with ThreadPoolExecutor(max_workers=nthr) as pool:
+        for f in [pool.submit(work, s, e) for s, e in spans]:
+            f.result()                                   # re-raises a worker's exception
+
+
 # ------------------------------------------------------------------------ warpings
 @dataclass(frozen=True)
 class DelReyWarping:
@@ -212,8 +229,8 @@ def build_mapP(xyzf, FToF, nfaces, limits, tol=1e-7, chunk=65536):
     pidx = pk * nfaces + pf
     mapP = np.empty((N_e * nfaces, npf), dtype=np.int64)
     scale = float(np.max(L))
-    for s in range(0, N_e * nfaces, chunk):
-        e = min(s + chunk, N_e * nfaces)
+
+    def work(s, e):
         A = X[s:e]                                            # (C, npf, d)
         Bn = X[pidx[s:e]]
         # shift the partner face by whole periods so the two faces coincide
@@ -232,6 +249,8 @@ def build_mapP(xyzf, FToF, nfaces, limits, tol=1e-7, chunk=65536):
         if npf > 1 and np.any(np.sort(arg, axis=1) != np.arange(npf)[None, :]):
             raise RuntimeError("facet node matching is not a permutation")
         mapP[s:e] = arg + (pf[s:e] * npf)[:, None] + (pk[s:e] * N_f)[:, None]
+
+    run_chunks(work, N_e * nfaces, min(chunk, 16384))
     # back to (N_f, N_e)
     return np.ascontiguousarray(mapP.reshape(N_e, nfaces * npf).T)
 

@@ -16,6 +16,7 @@ import numpy as np
 
 from . import conservation_laws as cl
 from . import grid_functions as gfn
+from .mesh import run_chunks
 from .geometric_factors import SpatialDiscretization, apply_reference_mapping
 from .linear_maps import (IdentityMap, SelectionMap, WarpedTensorProductMap2D,
                           WarpedTensorProductMap3D)
@@ -155,23 +156,30 @@ def get_dof(sd: SpatialDiscretization, law) -> Tuple[int, int, int]:
 # ---- initial data (Solvers.jl:389-428) ------------------------------------------------
 def project_function(initial_data, sd: SpatialDiscretization) -> np.ndarray:
     """Nodal: point values; modal: per-element L2 projection (VᵀWJV) \\ VᵀWJ u_q.
-    Returns u0 as (N_e, N_c, N_p) -- memory-identical to Julia's (N_p, N_c, N_e)."""
+    Returns u0 as (N_e, N_c, N_p) -- memory-identical to Julia's (N_p, N_c, N_e).
+    Elements are independent: chunks of them run on a thread pool (NumPy releases the GIL)."""
     ra = sd.reference_approximation
-    xq = tuple(x.T for x in sd.mesh.xyzq)                     # (N_e, N_q)
-    u_q = gfn.evaluate(initial_data, xq, 0.0)                 # (N_c, N_e, N_q)
-    u_q = np.ascontiguousarray(u_q.transpose(1, 0, 2))        # (N_e, N_c, N_q)
-    if isinstance(ra.V, IdentityMap):
-        return u_q
-    V = ra.V.to_dense()
+    nodal = isinstance(ra.V, IdentityMap)
+    V = None if nodal else ra.V.to_dense()
     J_q = sd.geometric_factors.J_q
-    u0 = np.empty((sd.N_e, u_q.shape[1], ra.N_p))
-    chunk = 32768
-    for s in range(0, sd.N_e, chunk):
-        e = min(s + chunk, sd.N_e)
+    xyzq = sd.mesh.xyzq                                       # d arrays (N_q, N_e)
+    N_e = sd.N_e
+    probe = gfn.evaluate(initial_data, tuple(x[:, :1].T for x in xyzq), 0.0)
+    N_c = probe.shape[0]
+    u0 = np.empty((N_e, N_c, ra.N_q if nodal else ra.N_p))
+
+    def work(s, e):
+        xq = tuple(x[:, s:e].T for x in xyzq)                 # (C, N_q)
+        u_q = gfn.evaluate(initial_data, xq, 0.0)             # (N_c, C, N_q)
+        if nodal:
+            u0[s:e] = u_q.transpose(1, 0, 2)
+            return
         VW = V.T[None, :, :] * (ra.W[None, :] * J_q[s:e])[:, None, :]   # (C, N_p, N_q)
         M = VW @ V
-        rhs = VW @ u_q[s:e].transpose(0, 2, 1)                          # (C, N_p, N_c)
+        rhs = VW @ u_q.transpose(1, 2, 0)                               # (C, N_p, N_c)
         u0[s:e] = np.linalg.solve(M, rhs).transpose(0, 2, 1)
+
+    run_chunks(work, N_e, 8192)
     return u0
 
 
