@@ -34,8 +34,8 @@ import numpy as np  # noqa: E402
 FLOP_PER_ELT = {"loop_b": 133.5e3 + 221.0e3, "loop_a": 75.0e3, "residual": 430.0e3}
 BYTES_PER_ELT_LOOP_B = 8 * (625 + 1125 + 125 + 300 + 100 + 500 + 500 + 175) + 4 * 100
 # dram__bytes_read.sum + dram__bytes_write.sum of the loop-B kernel per element, from the
-# `ncu --set full` capture at M=16 (profiles/r1_fluxdiff_tensor_v8.md): 591.8 MB / 24 576
-TRAFFIC_PER_ELT_LOOP_B = 24080.0
+# `ncu --set full` capture at M=16 (profiles/r1_fluxdiff_tensor_v12.md): 590.6 MB / 24 576
+TRAFFIC_PER_ELT_LOOP_B = 24032.0
 
 
 def read_peaks():
