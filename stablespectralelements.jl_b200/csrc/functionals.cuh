@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128)
 k_functional(Tables T, Geo G, Phys P, int which, const double* __restrict__ xa,
              const double* __restrict__ xb, double* __restrict__ partial, int n_out) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Np = T.N_p, Nq = T.N_q;
   int wt = 1;
   for (int m = 0; m < DIM; ++m) wt *= (T.n1 > 0 ? T.n1 : 1);

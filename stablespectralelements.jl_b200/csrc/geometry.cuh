@@ -9,7 +9,9 @@
 //   J_q (N_q, N_e); Lambda_q (N_q, d, d, N_e) = J dxi_l/dx_m at [i, l, m, k];
 //   J_f (N_f, N_e); nJf (d, N_f, N_e).
 #pragma once
+#ifndef SSE_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 namespace sse {
 
@@ -74,7 +76,7 @@ template <int DIM>
 __global__ void __launch_bounds__(128)
 k_geometry_exact(MapOps M, long long N_e, double* __restrict__ J_q, double* __restrict__ L_q,
                  double* __restrict__ J_f, double* __restrict__ nJf) {
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Nm = M.Nm, Nq = M.Nq, Nf = M.Nf;
   double* X = sm;
   double* dX = X + DIM * Nm;
@@ -137,7 +139,7 @@ k_geometry_exact(MapOps M, long long N_e, double* __restrict__ J_q, double* __re
 __global__ void __launch_bounds__(128)
 k_geometry_curl3d(MapOps M, long long N_e, double* __restrict__ J_q, double* __restrict__ L_q,
                   double* __restrict__ J_f, double* __restrict__ nJf) {
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Nm = M.Nm, Nm1 = M.Nm1, Nq = M.Nq, Nf = M.Nf;
   double* X = sm;
   double* dX = X + 3 * Nm;

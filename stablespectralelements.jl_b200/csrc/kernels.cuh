@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256)
 k_nodal_values(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
                double* __restrict__ u_f, int E, int proj) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
-  extern __shared__ double sm[];
+  SSE_SHARED(sm);
   const int Np = T.N_p, Nq = T.N_q, Nf = T.N_f;
   double* bufP = sm;
   double* bufQ = bufP + E * NC * Np;
@@ -450,7 +450,7 @@ k_fluxdiff(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NS = LawTraits<DIM, LAW>::NS;
   constexpr int DD = DIM * DIM;
-  extern __shared__ double sm[];
+  SSE_SHARED(sm);
   const int Np = T.N_p, Nq = T.N_q, Nf = T.N_f;
   double* sP = sm;
   double* sL = sP + E * NS * Nq;
@@ -601,7 +601,7 @@ k_standard_ref(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NS = LawTraits<DIM, LAW>::NS;
   constexpr int DD = DIM * DIM;
-  extern __shared__ double sm[];
+  SSE_SHARED(sm);
   const int Np = T.N_p, Nq = T.N_q, Nf = T.N_f;
   double* sH = sm;                              // hWΛ, index (m + DIM*n)
   double* sFq = sH + E * DD * Nq;
@@ -726,7 +726,7 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
            double* __restrict__ dudt, int E, int stage, int second_order) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NS = LawTraits<DIM, LAW>::NS;
-  extern __shared__ double sm[];
+  SSE_SHARED(sm);
   const int Np = T.N_p, Nq = T.N_q, Nf = T.N_f;
   double* sFq = sm;                              // [E][D][NC][N_q]
   double* sFn = sFq + E * DIM * NC * Nq;         // [E][D][NC][N_f] (stage 0) / [E][NC][N_f]

@@ -391,7 +391,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   using Cf = NodalCfg<DIM, N1>;
   constexpr int E = Cf::E;
   constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Np = T.N_p;
   double* bufQ = sm;
   double* tmp = bufQ + E * NC * NQ;
@@ -405,10 +405,10 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     const long long kp = k0 + G.pf_dist;
     if (kp + E <= G.N_e) {
       for (int o = threadIdx.x * 128; o < E * NC * Np * 8; o += 128 * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(u + kp * NC * Np) + o));
+        SSE_PREFETCH_L2((const char*)(u + kp * NC * Np) + o);
       if (proj == 2)
         for (int o = threadIdx.x * 128; o < E * NQ * 8; o += 128 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(G.J_q + kp * NQ) + o));
+          SSE_PREFETCH_L2((const char*)(G.J_q + kp * NQ) + o);
     }
   }
   // own node's Jacobian for the two weightings of the projection (thread = volume node)
@@ -521,7 +521,7 @@ k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restric
   static_assert(LawTraits<DIM, LAW>::NC == 1, "scalar conservation laws only");
   constexpr int NQ = ipow(N1, DIM);
   constexpr int Nf = TensorNF<DIM, N1, COLLAPSED>::value;
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Np = T.N_p;
   double* bufQ = sm;
   double* tmp = bufQ + NB * NQ;
@@ -597,7 +597,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
   constexpr int NC = Cf::NC, NS2 = Cf::NS2, NQ = Cf::NQ, NF = Cf::NF;
   constexpr int DD = DIM * DIM, H = Cf::H, KH = Cf::KH, EL = Cf::EL, nq = Cf::nq, nf = Cf::nf;
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Np = T.N_p;
   double2* sS2 = reinterpret_cast<double2*>(sm + Cf::oS);
   double2* sLa = reinterpret_cast<double2*>(sm + Cf::oLa);
@@ -622,7 +622,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     if (kp + EL <= G.N_e) {
       auto pf = [&](const void* base, int bytes) {
         for (int o = tid * 128; o < bytes; o += 128 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)base + o));
+          SSE_PREFETCH_L2((const char*)base + o);
       };
       pf(u_q + kp * NC * NQ, EL * NC * NQ * 8);
       pf(G.L_q + kp * DD * NQ, EL * DD * NQ * 8);
@@ -941,7 +941,7 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   using Cf = STCfg<DIM, N1, LAW, KC, NB>;
   constexpr int NQ = Cf::NQ, NF = Cf::NF;
   constexpr int DD = DIM * DIM;
-  extern __shared__ __align__(16) double sm[];
+  SSE_SHARED16(sm);
   const int Np = T.N_p;
   double* sPhi = sm + Cf::oPhi;
   double* sG = sm + Cf::oG;

@@ -11,6 +11,20 @@
 #pragma once
 #include <math.h>
 
+// Kernel-launch and dynamic-shared-memory spellings.  The one place they differ is the host
+// emulation build of the test suite (tests/emu/cuda_emu.h defines them before this header is
+// seen and runs every CUDA thread as a fiber); under nvcc they are the plain CUDA syntax.
+#ifndef SSE_HOST_EMU
+#define SSE_LAUNCH(...) <<<__VA_ARGS__>>>
+#define SSE_SHARED(name) extern __shared__ double name[]
+#define SSE_SHARED16(name) extern __shared__ __align__(16) double name[]
+#define SSE_RCP_APPROX(y, x) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x))
+#define SSE_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define SSE_RCP_APPROX(y, x) y = emu_rcp_approx(x)
+#define SSE_PREFETCH_L2(p) ((void)(p))
+#endif
+
 namespace sse {
 
 enum { LAW_ADV = 0, LAW_BURGERS = 1, LAW_EULER = 2 };
@@ -37,7 +51,7 @@ template <int DIM, int LAW> struct LawTraits {
 // normal, finite, non-zero arguments that occur here (densities, pressures, Jacobians).
 __device__ __forceinline__ double frcp(double x) {
   double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  SSE_RCP_APPROX(y, x);
   double e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
@@ -49,7 +63,7 @@ __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b);
 // enters through f^2 < 1e-4 (see logmean below)
 __device__ __forceinline__ double frcp1(double x) {
   double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  SSE_RCP_APPROX(y, x);
   double e = fma(-x, y, 1.0);
   return fma(y, e, y);
 }

@@ -4,7 +4,11 @@
 // device-resident buffers once (north-star part (d)), derives the operator bundles the
 // reference builds in Solvers/operators.jl (S, C = R^T B, transposes), and launches the
 // element kernels of kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#ifdef SSE_HOST_EMU
+#include "cuda_emu.h"   // tests/emu: host emulation of the execution model, test builds only
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -160,7 +164,7 @@ static int launch_a(sse_handle* h, const double* u_dev) {
   CU(cudaFuncSetAttribute(k_nodal_values<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)h->smem_a));
   int grid = (int)((h->G.N_e - h->G.k_begin + h->E_a - 1) / h->E_a);
-  k_nodal_values<DIM, LAW><<<grid, h->thr_a, h->smem_a, h->stream>>>(h->T, h->G, h->P, u_dev,
+  k_nodal_values<DIM, LAW> SSE_LAUNCH(grid, h->thr_a, h->smem_a, h->stream)(h->T, h->G, h->P, u_dev,
                                                                      h->u_q, h->u_f, h->E_a,
                                                                      h->proj);
   h->launches++;
@@ -176,7 +180,7 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
                             (int)h->smem_b));
     if (h->second_order && (h->b_stages & 1)) {
       RK none{};
-      k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+      k_physical<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(
           h->T, h->G, h->P, none, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 0, 1);
       h->launches++;
       if (!(h->b_stages & 2)) {
@@ -184,18 +188,18 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
         return 0;
       }
     }
-    k_physical<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+    k_physical<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(
         h->T, h->G, h->P, rk, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 1,
         h->second_order);
   } else if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
     CU(cudaFuncSetAttribute(k_fluxdiff<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)h->smem_b));
-    k_fluxdiff<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(h->T, h->G, h->P, rk, h->u_q,
+    k_fluxdiff<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(h->T, h->G, h->P, rk, h->u_q,
                                                                    h->u_f, dudt_dev, h->E_b);
   } else {
     CU(cudaFuncSetAttribute(k_standard_ref<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)h->smem_b));
-    k_standard_ref<DIM, LAW><<<grid, h->thr_b, h->smem_b, h->stream>>>(
+    k_standard_ref<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(
         h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->E_b);
   }
   h->launches++;
@@ -229,7 +233,7 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
       CU(cudaFuncSetAttribute(k_nodal_batched<DIM, N1, LAW, true, NB>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
-      k_nodal_batched<DIM, N1, LAW, true, NB><<<grid, 128, smem, h->stream>>>(h->T, h->G, u_dev,
+      k_nodal_batched<DIM, N1, LAW, true, NB> SSE_LAUNCH(grid, 128, smem, h->stream)(h->T, h->G, u_dev,
                                                                              h->u_q, h->u_f);
       h->launches++;
       CU(cudaGetLastError());
@@ -246,7 +250,7 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
     const char* e = getenv("SSE_B200_PREFETCH");
     h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_NODAL_MINB * EL;
   }
-  k_nodal_tensor<DIM, N1, LAW, true><<<grid, 128, smem, h->stream>>>(
+  k_nodal_tensor<DIM, N1, LAW, true> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
   h->launches++;
   CU(cudaGetLastError());
@@ -267,7 +271,7 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
     const char* e = getenv("SSE_B200_PREFETCH");
     h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_FD_MINB * Cf::EL;
   }
-  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC><<<grid, 128, smem, h->stream>>>(
+  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
   CU(cudaGetLastError());
@@ -282,7 +286,7 @@ static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, KC, NB>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
-  k_standard_tensor<DIM, N1, LAW, KC, NB><<<grid, 128, smem, h->stream>>>(
+  k_standard_tensor<DIM, N1, LAW, KC, NB> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
   CU(cudaGetLastError());
@@ -353,7 +357,7 @@ static int launch_functional(sse_handle* h, int which, const double* xa, const d
                           (int)smem));
   Geo G = h->G;
   G.k_begin = 0;
-  k_functional<DIM, LAW><<<(unsigned)h->cfg.N_e, 128, smem, h->stream>>>(h->T, G, h->P, which, xa,
+  k_functional<DIM, LAW> SSE_LAUNCH((unsigned)h->cfg.N_e, 128, smem, h->stream)(h->T, G, h->P, which, xa,
                                                                          xb, partial, n_out);
   h->launches++;
   CU(cudaGetLastError());
@@ -368,7 +372,12 @@ static int run_functional(sse_handle* h, int which, const double* xa, const doub
 extern "C" {
 
 const char* sse_last_error(void) { return g_err.c_str(); }
+// (negative: a host-emulation test build, which device.load_library refuses to use)
+#ifdef SSE_HOST_EMU
+int sse_version(void) { return -100; }
+#else
 int sse_version(void) { return 100; }
+#endif
 
 int sse_destroy(sse_handle* h) {
   if (!h) return 0;
@@ -1175,7 +1184,7 @@ int sse_halo_pack(sse_handle* h) {
   if (h->n_send == 0) return 0;
   CU(cudaSetDevice(h->cfg.device));
   int n = (int)h->n_send;
-  k_halo_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(h->u_f, h->send_off, n, h->cfg.N_c,
+  k_halo_pack SSE_LAUNCH((n + 255) / 256, 256, 0, h->stream)(h->u_f, h->send_off, n, h->cfg.N_c,
                                                       h->cfg.N_f, h->send_buf);
   h->launches++;
   CU(cudaGetLastError());
@@ -1187,7 +1196,7 @@ int sse_halo_unpack(sse_handle* h) {
   if (h->cfg.N_halo == 0) return 0;
   CU(cudaSetDevice(h->cfg.device));
   int n = (int)h->cfg.N_halo;
-  k_halo_unpack<<<(n + 255) / 256, 256, 0, h->stream>>>(h->u_f, h->recv_buf, n, h->cfg.N_c,
+  k_halo_unpack SSE_LAUNCH((n + 255) / 256, 256, 0, h->stream)(h->u_f, h->recv_buf, n, h->cfg.N_c,
                                                         h->cfg.N_f, h->cfg.N_e);
   h->launches++;
   CU(cudaGetLastError());
@@ -1232,7 +1241,7 @@ int sse_halo_pack_aux(sse_handle* h) {
   if (h->n_send == 0) return 0;
   CU(cudaSetDevice(h->cfg.device));
   int n = (int)h->n_send;
-  k_halo_pack_aux<<<(n + 255) / 256, 256, 0, h->stream>>>(h->q_f, h->send_off, n, h->cfg.N_c,
+  k_halo_pack_aux SSE_LAUNCH((n + 255) / 256, 256, 0, h->stream)(h->q_f, h->send_off, n, h->cfg.N_c,
                                                           h->cfg.dim, h->cfg.N_f, h->send_buf);
   h->launches++;
   CU(cudaGetLastError());
@@ -1245,7 +1254,7 @@ int sse_halo_unpack_aux(sse_handle* h) {
   if (h->cfg.N_halo == 0) return 0;
   CU(cudaSetDevice(h->cfg.device));
   int n = (int)h->cfg.N_halo;
-  k_halo_unpack_aux<<<(n + 255) / 256, 256, 0, h->stream>>>(h->q_f, h->recv_buf, n, h->cfg.N_c,
+  k_halo_unpack_aux SSE_LAUNCH((n + 255) / 256, 256, 0, h->stream)(h->q_f, h->recv_buf, n, h->cfg.N_c,
                                                             h->cfg.dim, h->cfg.N_f, h->cfg.N_e);
   h->launches++;
   CU(cudaGetLastError());
@@ -1313,7 +1322,7 @@ int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host
   std::vector<double> hb((size_t)nblk * n_out);
   if (!rc) rc = run_functional(h, which, xa, xb, partial, n_out);
   if (!rc) {
-    k_reduce_partials<<<nblk, 256, 0, h->stream>>>(partial, Ne, n_out, chunk, blocks);
+    k_reduce_partials SSE_LAUNCH(nblk, 256, 0, h->stream)(partial, Ne, n_out, chunk, blocks);
     h->launches++;
     if (cudaMemcpyAsync(hb.data(), blocks, hb.size() * sizeof(double), cudaMemcpyDeviceToHost,
                         h->stream) != cudaSuccess ||
@@ -1381,18 +1390,18 @@ int sse_geometry_build(const sse_mapping* m, sse_geometry* out) {
     if (curl) {
       const size_t smem = sizeof(double) * ((size_t)13 * Nm + (size_t)24 * Nm1);
       cudaFuncSetAttribute(k_geometry_curl3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_geometry_curl3d<<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+      k_geometry_curl3d SSE_LAUNCH((unsigned)Ne, 128, smem)(M, Ne, Jq, Lq, Jf, nJ);
     } else {
       const size_t smem = sizeof(double) * ((size_t)(d + d * d) * Nm + Nq);
       if (d == 1) {
         cudaFuncSetAttribute(k_geometry_exact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_geometry_exact<1><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+        k_geometry_exact<1> SSE_LAUNCH((unsigned)Ne, 128, smem)(M, Ne, Jq, Lq, Jf, nJ);
       } else if (d == 2) {
         cudaFuncSetAttribute(k_geometry_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_geometry_exact<2><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+        k_geometry_exact<2> SSE_LAUNCH((unsigned)Ne, 128, smem)(M, Ne, Jq, Lq, Jf, nJ);
       } else {
         cudaFuncSetAttribute(k_geometry_exact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_geometry_exact<3><<<(unsigned)Ne, 128, smem>>>(M, Ne, Jq, Lq, Jf, nJ);
+        k_geometry_exact<3> SSE_LAUNCH((unsigned)Ne, 128, smem)(M, Ne, Jq, Lq, Jf, nJ);
       }
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -1484,7 +1493,7 @@ int sse_measure_fp64_peak(int device, double* tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 6; ++rep) {
     CU(cudaEventRecord(e0));
-    k_fp64_peak<<<blocks, threads>>>(out, iters, 1.0);
+    k_fp64_peak SSE_LAUNCH(blocks, threads)(out, iters, 1.0);
     CU(cudaEventRecord(e1));
     CU(cudaEventSynchronize(e1));
     float ms = 0.f;

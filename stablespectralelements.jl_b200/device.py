@@ -76,8 +76,11 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_halo_pack_aux", "sse_halo_unpack_aux"]
 
 
-def load_library(path: Optional[str] = None):
-    """Load libsse_b200.so; raises if it has not been built (no fallback)."""
+def load_library(path: Optional[str] = None, allow_emulation: bool = False):
+    """Load libsse_b200.so; raises if it has not been built (no fallback).
+
+    A host-emulation build of the kernels (tests/emu, ``sse_version() < 0``) is test
+    infrastructure: it is refused unless the caller -- a test -- asks for it explicitly."""
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
@@ -89,6 +92,9 @@ def load_library(path: Optional[str] = None):
     vp = C.c_void_p
     lib.sse_last_error.restype = C.c_char_p
     lib.sse_version.restype = C.c_int
+    if lib.sse_version() < 0 and not allow_emulation:
+        raise RuntimeError(f"{p} is a host-emulation test build of the kernels, not the CUDA "
+                           f"library: the residual has no CPU fallback")
     lib.sse_create.argtypes = [C.POINTER(SseConfig), C.POINTER(SseOperators),
                                C.POINTER(SseGeometry), c_i64_p, C.POINTER(vp)]
     lib.sse_destroy.argtypes = [vp]

@@ -1,0 +1,37 @@
+"""Build tests/emu/_build/libsse_b200_emu.so: the CUDA sources of the product compiled with g++
+against tests/emu/cuda_emu.h (-DSSE_HOST_EMU), every CUDA thread a fiber.  Test infrastructure
+only -- see the header of cuda_emu.h."""
+import hashlib
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "stablespectralelements.jl_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libsse_b200_emu.so")
+CMD = ["g++", "-O1", "-std=c++17", "-DSSE_HOST_EMU", "-x", "c++", "-I", HERE, "-fPIC", "-shared"]
+
+
+def _digest():
+    h = hashlib.sha256(" ".join(CMD).encode())
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files += [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "sse_b200.h")]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build() -> str:
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    stamp, dig = OUT + ".stamp", _digest()
+    if os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return OUT
+    subprocess.run(CMD + ["-o", OUT, os.path.join(CSRC, "sse_b200.cu"), "-ldl"], check=True, cwd=CSRC)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build())
