@@ -143,17 +143,23 @@ class DistributedResidual:
                 self.dev = DeviceResidual(solver, device=device, mapP=self.part.mapP_local,
                                           n_halo=self.part.n_halo, elements=self.elements)
             self.dev.halo_setup(self.part.send_idx)
-            s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
-            # doubles per trace node: N_c for u_f, dim * N_c for the BR1 auxiliary traces q_f
-            width = self.dev.N_c * (self.dim if self.second_order else 1)
-            dv = torch.device("cuda", device)
-            self.send_t = torch.as_tensor(_DevBuf(s_ptr, n_s * width), device=dv)
-            self.recv_t = torch.as_tensor(_DevBuf(r_ptr, n_r * width), device=dv)
-            # run the library on torch's current stream so NCCL ordering is stream-ordered
-            self.dev.set_stream(torch.cuda.current_stream(dv).cuda_stream)
+            self._attach_buffers(device)
             self._ops = None
         self.local_shape = self.dev.shape
         self.n_local_state = int(np.prod(self.local_shape))
+
+    def _attach_buffers(self, device: int):
+        """Wrap the library's packed send / receive buffers as torch CUDA tensors (what NCCL
+        sends from / receives into) and run the library on torch's current stream so that the
+        NCCL ordering is stream-ordered."""
+        torch = self.torch
+        s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
+        # doubles per trace node: N_c for u_f, dim * N_c for the BR1 auxiliary traces q_f
+        width = self.dev.N_c * (self.dim if self.second_order else 1)
+        dv = torch.device("cuda", device)
+        self.send_t = torch.as_tensor(_DevBuf(s_ptr, n_s * width), device=dv)
+        self.recv_t = torch.as_tensor(_DevBuf(r_ptr, n_r * width), device=dv)
+        self.dev.set_stream(torch.cuda.current_stream(dv).cuda_stream)
 
     # ------------------------------------------------------------------ plumbing
     def halo_segments(self, width: int):

@@ -102,6 +102,10 @@ inline Pool& pool() {
   static Pool p;
   return p;
 }
+inline int& order_mode() {   // 0: ascending thread index, 1: descending, 2: a scrambled order
+  static int m = 0;
+  return m;
+}
 inline std::function<void()>*& body_slot() {
   static std::function<void()>* b = nullptr;
   return b;
@@ -144,9 +148,16 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
           makecontext(&P.ctx[t], (void (*)())fiber_main, 1, t);
         }
         int remaining = nthr;
+        unsigned pass = 0;
         while (remaining > 0) {       // one pass = one barrier interval
           remaining = 0;
-          for (int t = 0; t < nthr; ++t) {
+          ++pass;
+          for (int q = 0; q < nthr; ++q) {
+            // thread order inside a barrier interval: results must not depend on it, so running
+            // the suite with another order (emu_set_order) is a shared-memory race check
+            int t = q;
+            if (order_mode() == 1) t = nthr - 1 - q;
+            else if (order_mode() == 2) t = (int)(((unsigned long long)q * 61u + 17u * pass) % (unsigned)nthr);
             if (P.done[t]) continue;
             s.current = t;
             s.tIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
@@ -284,3 +295,5 @@ extern "C" __attribute__((used)) const char* emu_launch_log() {
   emu::launch_log().clear();
   return out.c_str();
 }
+
+extern "C" __attribute__((used)) void emu_set_order(int mode) { emu::order_mode() = mode; }

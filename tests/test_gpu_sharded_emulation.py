@@ -24,12 +24,13 @@ def _local_exchange(shards, width):
                 continue
             snd = shards[peer].halo_segments(width)[dst.rank][0]
             assert snd.stop - snd.start == rcv.stop - rcv.start
-            dst.recv_t[rcv].copy_(shards[peer].send_t[snd])
+            dst.recv_t[rcv] = shards[peer].send_t[snd]
 
 
-def _run_sharded(solver, u, world):
+def _run_sharded(solver, u, world, shard_cls=None):
     from sse_b200.distributed import DistributedResidual
-    shards = [DistributedResidual(solver, rank=r, world=world, device=0) for r in range(world)]
+    shard_cls = shard_cls or DistributedResidual
+    shards = [shard_cls(solver, rank=r, world=world, device=0) for r in range(world)]
     try:
         for sh in shards:
             sh.set_state(np.ascontiguousarray(u[sh.elements]))
@@ -67,7 +68,7 @@ CASES = {
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_sharded_flow_matches_single_domain(name, world):
+def test_sharded_flow_matches_single_domain(name, world, shard_cls=None):
     from sse_b200.distributed import DistributedResidual
     build, n_exch = CASES[name]
     solver, u0 = build()
@@ -79,7 +80,7 @@ def test_sharded_flow_matches_single_domain(name, world):
         ref_gpu = whole.get_dudt()
     finally:
         whole.close()
-    got, n = _run_sharded(solver, u, world)
+    got, n = _run_sharded(solver, u, world, shard_cls)
     assert n == n_exch
     assert np.array_equal(got, ref_gpu)
     ref = oc.semi_discrete_residual(oracle_problem(solver), u)

@@ -101,3 +101,105 @@ def test_product_loader_refuses_emulation_build(emu_lib):
             dev.load_library(build_emu.build())
     finally:
         dev._LIB = saved
+
+
+# ---------------------------------------------------------------------------------------
+# The bodies of the GPU test modules, run against the emulated library: everything below goes
+# through the same Python host code, C ABI and kernels as on a B200.
+def test_functionals_in_emulation(emu_lib):
+    import test_gpu_functionals as tf
+    for name in ("euler3d_tet_p3_warp_ec", "advdiff1d_p4", "adv2d_tri_p4_central"):
+        tf.test_functionals_match_oracle(name)
+
+
+def test_golden_fixtures_in_emulation(emu_lib):
+    import test_golden_fixtures as tg
+    for name in sorted(tg.mg.FIXTURES):
+        tg.test_cuda_reproduces_fixture(name)
+
+
+def test_device_resident_ck54_in_emulation(emu_lib):
+    """sse_rk_step_ck54 (fused 2N Runge-Kutta epilogue) reproduces the reference's golden L2
+    error of the 1-D advection-diffusion case (runtests.jl:14-36) when run on the emulator."""
+    from sse_b200.solvers import ODEProblem, semi_discrete_residual as f
+    from sse_b200.time_integration import CarpenterKennedy2N54, solve
+    solver, u0, T, dt, exact, gold = gc.advection_diffusion_1d(lazy=False)
+    try:
+        u = solve(ODEProblem(f, u0, (0.0, T), solver), CarpenterKennedy2N54(), dt=dt)
+        prob = oracle_problem(solver)
+        xq = tuple(x.T for x in solver.spatial_discretization.mesh.xyzq)
+        l2 = oc.l2_error(prob, u, np.stack(exact(*xq, T), axis=-1))
+        assert np.max(np.abs(l2 - np.array(gold))) < 1e-10, (l2, gold)
+    finally:
+        solver.close()
+
+
+def _emu_shard_class():
+    from sse_b200.distributed import DistributedResidual
+
+    class EmuShard(DistributedResidual):
+        """A shard whose packed halo buffers are NumPy views of the emulator's host memory."""
+
+        def _attach_buffers(self, device):
+            s_ptr, r_ptr, n_s, n_r = self.dev.halo_buffers()
+            width = self.dev.N_c * (self.dim if self.second_order else 1)
+            view = lambda ptr, n: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)),
+                                                        shape=(n,))
+            self.send_t, self.recv_t = view(s_ptr, n_s * width), view(r_ptr, n_r * width)
+
+    return EmuShard
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["advdiff1d_p4_br1", "advdiff2d_p3_br1", "euler3d_tet_p2",
+                                  "adv3d_tet_p2"])
+def test_sharded_flow_in_emulation(emu_lib, name, world):
+    """DistributedResidual._flow (pack, exchange, interior / boundary ranges; two exchanges for
+    BR1) with sse_halo_pack/unpack(_aux) and the range launches, on 2-3 emulated shards."""
+    import test_gpu_sharded_emulation as ts
+    ts.test_sharded_flow_matches_single_domain(name, world, shard_cls=_emu_shard_class())
+
+
+def test_device_geometry_in_emulation(emu_lib):
+    """sse_geometry_build (exact and conservative-curl metrics, Jacobian projection) on the
+    emulator against the host restatement, and a residual assembled from those pointers."""
+    import test_gpu_geometry as tg
+    for case in tg._meshes():
+        tg.test_device_geometry_matches_host(case)
+    tg.test_residual_from_device_geometry_matches_host_geometry()
+
+
+def test_parity_module_in_emulation(emu_lib):
+    """tests/test_gpu_parity.py's checks (input untouched, second call reproduces the first,
+    EC-flux entropy conservation, error paths) against the emulated library."""
+    import test_gpu_parity as tp
+    for name in ("euler3d_tet_p4_warp_ec", "euler2d_tri_p3_nodal", "golden_adv3d_tet_dense_V",
+                 "golden_burgers1d", "advdiff1d_p8"):
+        tp.test_residual_matches_oracle(name)
+    tp.test_entropy_conservation_ec_flux_tet()
+    tp.test_error_paths()
+
+
+@pytest.mark.parametrize("name", ["euler3d_tet_p4_warp_lf", "adv3d_tet_p4", "euler2d_tri_p4_lf",
+                                  "advdiff2d_p3", "euler3d_hex_nodal_p3_ec"])
+def test_no_shared_memory_races(emu_lib, name):
+    """Race check: between two barriers the result must not depend on the order in which the
+    threads of a block run.  The emulator runs them in ascending, descending and a scrambled
+    order (for the scrambled one: 61 is coprime to every block size used); a missing
+    __syncthreads shows up as a difference.  Outputs must agree BITWISE."""
+    build, _ = CASES[name]
+    solver, u0 = build()
+    u = cases.rough_state(solver, u0, seed=2)
+    d = dev.DeviceResidual(solver)
+    outs = []
+    try:
+        for mode in (0, 1, 2):
+            emu_lib.emu_set_order(mode)
+            dudt = np.full_like(u, np.nan)
+            d.residual_host(u, dudt)
+            outs.append(dudt)
+    finally:
+        emu_lib.emu_set_order(0)
+        d.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
