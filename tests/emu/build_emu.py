@@ -22,15 +22,20 @@ def _digest():
     return h.hexdigest()
 
 
-def build() -> str:
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    stamp, dig = OUT + ".stamp", _digest()
-    if os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return OUT
-    subprocess.run(CMD + ["-o", OUT, os.path.join(CSRC, "sse_b200.cu"), "-ldl"], check=True, cwd=CSRC)
+def build(asan: bool = False) -> str:
+    """``asan``: an AddressSanitizer build (every "device" buffer and the dynamic shared memory
+    of each launch are heap blocks, so out-of-bounds accesses of the kernels trap)."""
+    out = OUT.replace(".so", "_asan.so") if asan else OUT
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    stamp, dig = out + ".stamp", _digest() + ("-asan" if asan else "")
+    if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return out
+    subprocess.run(CMD + extra + ["-o", out, os.path.join(CSRC, "sse_b200.cu"), "-ldl"],
+                   check=True, cwd=CSRC)
     with open(stamp, "w") as f:
         f.write(dig)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

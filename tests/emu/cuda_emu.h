@@ -127,9 +127,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
     P.done.resize(nthr);
     P.stacks.resize((size_t)nthr * kStack);
   }
-  P.smem.assign(smem_bytes / sizeof(double) + 2, 0.0);
-  // a poison pattern instead of zeros: reads of never-written shared memory show up as NaN
-  for (auto& v : P.smem) v = std::nan("");
+  // exactly the dynamic shared memory the launch asked for (a fresh heap block, so that an
+  // AddressSanitizer build of the emulator traps accesses past its end), NaN-poisoned: reads of
+  // never-written shared memory show up as NaN
+  std::vector<double>(smem_bytes / sizeof(double), std::nan("")).swap(P.smem);
   s.smem = P.smem.data();
   s.bDim = block;
   s.gDim = grid;

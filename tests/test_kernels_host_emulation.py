@@ -203,3 +203,23 @@ def test_no_shared_memory_races(emu_lib, name):
         d.close()
     assert np.array_equal(outs[0], outs[1])
     assert np.array_equal(outs[0], outs[2])
+
+
+def test_kernels_address_sanitizer():
+    """Memory check: the emulated library built with -fsanitize=address runs one residual of
+    every kernel family, the device geometry and a sharded BR1 flow.  Every
+    "device" allocation and each launch's dynamic shared memory is its own heap block, so an
+    out-of-bounds access by a kernel (global or shared) is trapped."""
+    import subprocess
+    import build_emu
+    asan_rt = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
+                             text=True).stdout.strip()
+    if not os.path.isabs(asan_rt) or not os.path.exists(asan_rt):
+        pytest.skip("libasan not available")
+    lib = build_emu.build(asan=True)
+    env = dict(os.environ, LD_PRELOAD=asan_rt,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=0")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "asan_cases.py"), lib],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert r.returncode == 0 and "ASAN-CASES-DONE" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
