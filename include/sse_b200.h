@@ -139,6 +139,12 @@ int sse_get_state(sse_handle* h, double* u_host);
 int sse_state_ptr(sse_handle* h, double** u_dev, double** dudt_dev);
 int sse_rk_stage(sse_handle* h, double a, double b, double dt);
 int sse_rk_step_ck54(sse_handle* h, double dt);   /* Carpenter-Kennedy (5,4), 5 fused stages */
+/* One step of a general explicit Runge-Kutta scheme on the device-resident state -- what
+ * OrdinaryDiffEq's non-low-storage algorithms do around f(du,u,p,t), e.g. DP8 in the reference's
+ * 3-D Euler test (test/euler_3d.jl:44-51).  A: n_stages x n_stages row-major, strictly lower
+ * triangular; b: n_stages weights; at most 16 stages.  k_s = R(u + dt sum_j A[s][j] k_j),
+ * u <- u + dt sum_s b[s] k_s; the stage buffers are allocated on first use. */
+int sse_erk_step(sse_handle* h, int n_stages, const double* A, const double* b, double dt);
 
 /* Halo of facet traces for element-sharded runs.  send_idx: n_send linear indices (j + N_f*k)
  * of local trace nodes to pack; the packed buffer holds N_c doubles per index, node-major

@@ -886,6 +886,23 @@ __global__ void k_halo_unpack_aux(double* __restrict__ q_f, const double* __rest
   }
 }
 
+// out = base + sum_t c[t] * x[t]  (stage states and the final update of a general explicit
+// Runge-Kutta step, sse_erk_step); out may alias base
+#define SSE_ERK_MAX_TERMS 16
+struct LinComb {
+  int n;
+  double c[SSE_ERK_MAX_TERMS];
+  const double* x[SSE_ERK_MAX_TERMS];
+};
+__global__ void k_lincomb(double* out, const double* base, LinComb L, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double acc = base[i];
+    for (int t = 0; t < L.n; ++t) acc = fma(L.c[t], L.x[t][i], acc);
+    out[i] = acc;
+  }
+}
+
 __global__ void k_axpy_rk(double* __restrict__ u, double* __restrict__ k, const double* r,
                           double a, double b, double dt, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -79,6 +79,9 @@ struct sse_handle {
   int64_t n_send = 0;
   // launch configuration
   int second_order = 0, proj = 0, law_t = 0;
+  double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
+  double* erk_u = nullptr;      //               stage state
+  int erk_stages = 0;
   int b_stages = 3;   // second order: bit 0 = auxiliary_variable! (A2), bit 1 = time_derivative!
   int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
   size_t smem_a = 0, smem_b = 0;
@@ -1148,6 +1151,52 @@ int sse_rk_step_ck54(sse_handle* h, double dt) {
                               2277821191437.0 / 14882151754819.0};
   for (int s = 0; s < 5; ++s)
     if (sse_rk_stage(h, A[s], B[s], dt)) return -1;
+  return 0;
+}
+
+// General explicit Runge-Kutta step on the device-resident state (the reference integrates with
+// OrdinaryDiffEq; its 3-D Euler test uses DP8, test/euler_3d.jl:44-51):
+//   k_s = R(u + dt sum_{j<s} A[s][j] k_j),   u <- u + dt sum_s b[s] k_s.
+int sse_erk_step(sse_handle* h, int n_stages, const double* A, const double* b, double dt) {
+  if (!h || !A || !b) return fail("null argument");
+  if (n_stages < 1 || n_stages > SSE_ERK_MAX_TERMS)
+    return fail("sse_erk_step: 1..%d stages supported", SSE_ERK_MAX_TERMS);
+  if (h->cfg.N_halo) return fail("sse_erk_step: element shards are stepped by the host framework");
+  for (int s = 0; s < n_stages; ++s)
+    for (int j = s; j < n_stages; ++j)
+      if (A[s * n_stages + j] != 0.0) return fail("sse_erk_step: the tableau must be explicit");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->erk_stages < n_stages) {      // (an earlier, smaller set stays owned by the handle)
+    if (dev_upload<double>(h, nullptr, (size_t)n_stages * h->n_state, &h->erk_k)) return -1;
+    if (!h->erk_u && dev_upload<double>(h, nullptr, (size_t)h->n_state, &h->erk_u)) return -1;
+    h->erk_stages = n_stages;
+  }
+  const long long n = h->n_state;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 16);
+  RK none{};
+  for (int s = 0; s <= n_stages; ++s) {
+    // s < n_stages: stage state into erk_u;  s == n_stages: the update of u itself
+    LinComb L{};
+    const double* coef = (s < n_stages) ? A + (size_t)s * n_stages : b;
+    const int terms = (s < n_stages) ? s : n_stages;
+    for (int j = 0; j < terms; ++j)
+      if (coef[j] != 0.0) {
+        L.c[L.n] = dt * coef[j];
+        L.x[L.n] = h->erk_k + (size_t)j * n;
+        ++L.n;
+      }
+    const double* u_stage = h->u;
+    if (s == n_stages || L.n > 0) {
+      double* out = (s < n_stages) ? h->erk_u : h->u;
+      k_lincomb SSE_LAUNCH(blocks, 256, 0, h->stream)(out, h->u, L, n);
+      h->launches++;
+      CU(cudaGetLastError());
+      u_stage = out;
+    }
+    if (s == n_stages) break;
+    if (run_a(h, u_stage)) return -1;
+    if (run_b(h, h->erk_k + (size_t)s * n, none)) return -1;
+  }
   return 0;
 }
 

@@ -73,7 +73,7 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_download_dudt_range", "sse_sync_copies", "sse_functional",
            "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host",
            "sse_auxiliary_variable_range", "sse_time_derivative_only_range",
-           "sse_halo_pack_aux", "sse_halo_unpack_aux"]
+           "sse_halo_pack_aux", "sse_halo_unpack_aux", "sse_erk_step"]
 
 
 def load_library(path: Optional[str] = None, allow_emulation: bool = False):
@@ -134,6 +134,7 @@ def load_library(path: Optional[str] = None, allow_emulation: bool = False):
     lib.sse_time_derivative_only_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
     lib.sse_halo_pack_aux.argtypes = [vp]
     lib.sse_halo_unpack_aux.argtypes = [vp]
+    lib.sse_erk_step.argtypes = [vp, C.c_int, c_d_p, c_d_p, C.c_double]
     if path is None:
         _LIB = lib
     return lib
@@ -409,6 +410,14 @@ class DeviceResidual:
 
     def rk_stage(self, a: float, b: float, dt: float):
         self._check(self.lib.sse_rk_stage(self.h, a, b, dt), "sse_rk_stage")
+
+    def erk_step(self, A: np.ndarray, b: np.ndarray, dt: float):
+        """One general explicit Runge-Kutta step (tableau A, weights b) on the resident state."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        if A.ndim != 2 or A.shape[0] != A.shape[1] or b.shape != (A.shape[0],):
+            raise ValueError("A must be (s, s) and b (s,)")
+        self._check(self.lib.sse_erk_step(self.h, A.shape[0], _dp(A), _dp(b), dt), "sse_erk_step")
 
     def rk_step_ck54(self, dt: float):
         self._check(self.lib.sse_rk_step_ck54(self.h, dt), "sse_rk_step_ck54")

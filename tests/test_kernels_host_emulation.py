@@ -223,3 +223,32 @@ def test_kernels_address_sanitizer():
                        capture_output=True, text=True, env=env, timeout=900)
     assert "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-3000:]
     assert r.returncode == 0 and "ASAN-CASES-DONE" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_general_explicit_rk_in_emulation(emu_lib):
+    """sse_erk_step (DP8: the integrator of the reference's 3-D Euler test, euler_3d.jl:44-51)
+    on the emulator: a few steps of the golden Hex case equal the oracle's DP8 to round-off; RK4
+    and DP5 show their orders on the 1-D advection-diffusion case."""
+    from sse_b200.solvers import ODEProblem, semi_discrete_residual as f
+    from sse_b200.time_integration import DP5, DP8, RK4, SSPRK33, solve
+    solver, u0, T, n_steps, exact, gold = gc.euler_3d_hex(lazy=False)
+    try:
+        dt = T / n_steps
+        u = solve(ODEProblem(f, u0, (0.0, 3 * dt), solver), DP8(), dt=dt)
+        prob = oracle_problem(solver)
+        ref = oc.dp8_integrate(lambda v, t: oc.semi_discrete_residual(prob, v, t), u0,
+                               (0.0, 3 * dt), 3)
+        assert _rel(u, ref) < 1e-13
+    finally:
+        solver.close()
+    solver, u0, T, dt, exact, gold = gc.advection_diffusion_1d(lazy=False)
+    try:
+        prob = oracle_problem(solver)
+        rhs = lambda v, t: oc.semi_discrete_residual(prob, v, t)
+        fine = oc.dp8_integrate(rhs, u0, (0.0, 0.02), 128)
+        for alg, order in ((RK4(), 4), (DP5(), 5), (SSPRK33(), 3)):
+            err = [np.max(np.abs(solve(ODEProblem(f, u0, (0.0, 0.02), solver), alg, dt=0.02 / n)
+                                 - fine)) for n in (8, 16)]
+            assert order - 0.6 < np.log2(err[0] / err[1]) < order + 0.8, (type(alg).__name__, err)
+    finally:
+        solver.close()
