@@ -49,6 +49,15 @@ static int fail(const char* fmt, ...) {
 
 #define SSE_MAX_CHUNKS 32
 
+// Tuning knobs of the scalar standard-form kernels (elements per CTA riding along as components);
+// the defaults are the measured optimum, tools/gpu_variants.sh sweeps -D overrides.
+#ifndef SSE_STD_NB
+#define SSE_STD_NB 4      // k_standard_tensor (loop B)
+#endif
+#ifndef SSE_NODAL_NB
+#define SSE_NODAL_NB 8    // k_nodal_batched (loop A)
+#endif
+
 struct sse_handle {
   sse_config cfg{};
   Tables T{};
@@ -231,7 +240,7 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
     return fail("facet-node count does not match the specialised kernel");
   if constexpr (DIM == 3 && LawTraits<DIM, LAW>::NC == 1) {
     if (h->proj == 0) {   // scalar law, no entropy projection: 8 elements per CTA as components
-      constexpr int NB = 8;
+      constexpr int NB = SSE_NODAL_NB;
       const size_t smem = NodalBatchCfg<DIM, N1, NB>::bytes(h->cfg.N_p, h->cfg.N_f);
       CU(cudaFuncSetAttribute(k_nodal_batched<DIM, N1, LAW, true, NB>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -329,9 +338,9 @@ static int run_a(sse_handle* h, const double* u_dev) {
 }
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
   switch (h->fast_std) {   // standard form, advection on collapsed simplices
-    case 303: return launch_std_fast<3, 3, LAW_ADV, 6, 4>(h, dudt_dev, rk);
-    case 304: return launch_std_fast<3, 4, LAW_ADV, 7, 4>(h, dudt_dev, rk);
-    case 305: return launch_std_fast<3, 5, LAW_ADV, 8, 4>(h, dudt_dev, rk);
+    case 303: return launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_NB>(h, dudt_dev, rk);
+    case 304: return launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_NB>(h, dudt_dev, rk);
+    case 305: return launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_NB>(h, dudt_dev, rk);
     default: break;
   }
   switch (h->fast_b) {

@@ -22,13 +22,16 @@ def _digest():
     return h.hexdigest()
 
 
-def build(asan: bool = False) -> str:
+def build(asan: bool = False, defines=()) -> str:
     """``asan``: an AddressSanitizer build (every "device" buffer and the dynamic shared memory
-    of each launch are heap blocks, so out-of-bounds accesses of the kernels trap)."""
-    out = OUT.replace(".so", "_asan.so") if asan else OUT
+    of each launch are heap blocks, so out-of-bounds accesses of the kernels trap).
+    ``defines``: extra -D tuning knobs (e.g. ("SSE_STD_NB=2",)) to check a kernel variant."""
+    tag = ("_asan" if asan else "") + "".join("_" + d.replace("=", "") for d in defines)
+    out = OUT.replace(".so", tag + ".so")
     extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    extra += ["-D" + d for d in defines]
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    stamp, dig = out + ".stamp", _digest() + ("-asan" if asan else "")
+    stamp, dig = out + ".stamp", _digest() + tag
     if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return out
     subprocess.run(CMD + extra + ["-o", out, os.path.join(CSRC, "sse_b200.cu"), "-ldl"],

@@ -60,6 +60,11 @@ CASES = {
     # standard form: specialised scalar kernels (elements as components) and generic ones
     "adv3d_tet_p4": (lambda: cases.advection_tet_case(p=4, M=2, lazy=True),
                      ["k_nodal_batchedILi3ELi5E", "k_standard_tensorILi3ELi5E"]),
+    # 162 elements: ragged last CTA of the batched kernels (8 and 4 elements per CTA)
+    "adv3d_tet_p4_ragged": (lambda: cases.advection_tet_case(p=4, M=3, lazy=True),
+                            ["k_nodal_batchedILi3ELi5E", "k_standard_tensorILi3ELi5E"]),
+    "adv3d_tet_p3_straight": (lambda: cases.advection_tet_case(p=3, M=3, lazy=True, warp=0.0),
+                              ["k_nodal_batchedILi3ELi4E", "k_standard_tensorILi3ELi4E"]),
     "adv2d_tri_p4": (lambda: cases.advection_tri_case(p=4, M=3, lazy=True), ["k_standard"]),
     "burgers2d_tri_p3_ec": (lambda: cases.burgers_tri_case(p=3, M=3, lazy=True), ["k_fluxdiff"]),
     "euler3d_hex_nodal_p3_ec": (lambda: cases.euler_hex_case(p=3, M=2, lazy=True),
@@ -252,3 +257,28 @@ def test_general_explicit_rk_in_emulation(emu_lib):
             assert order - 0.6 < np.log2(err[0] / err[1]) < order + 0.8, (type(alg).__name__, err)
     finally:
         solver.close()
+
+
+@pytest.mark.parametrize("defines", [("SSE_STD_NB=2", "SSE_NODAL_NB=4"),
+                                     ("SSE_FD_SINGLE_BUF=1", "SSE_FD_KQ=3")])
+def test_tuning_knob_variants_in_emulation(defines):
+    """The -D tuning knobs tools/gpu_variants.sh sweeps on the GPU (elements per CTA of the
+    scalar kernels, exchange-buffer layout of loop B) give the same residuals: checked here so
+    that a sweep spends GPU time on timing only."""
+    import build_emu
+    lib = dev.load_library(build_emu.build(defines=defines), allow_emulation=True)
+    saved, dev._LIB = dev._LIB, lib
+    try:
+        for name in ("adv3d_tet_p4_ragged", "euler3d_tet_p4_warp_lf"):
+            solver, u0 = CASES[name][0]()
+            u = cases.rough_state(solver, u0, seed=4)
+            d = dev.DeviceResidual(solver)
+            try:
+                dudt = np.full_like(u, np.nan)
+                d.residual_host(u, dudt)
+                ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+                assert _rel(dudt, ref) < 1e-12, (defines, name)
+            finally:
+                d.close()
+    finally:
+        dev._LIB = saved
