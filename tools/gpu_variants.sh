@@ -19,4 +19,8 @@ try:
 except Exception as e:
     print("$name", "FAILED", e)
 PY
+  # config 3 (scalar standard-form kernels: SSE_STD_NB / SSE_NODAL_NB variants)
+  if [ "${CFG3:-0}" = "1" ]; then
+    SSE_B200_LIB=$PWD/$lib CFG3_M=${CFG3_M:-32} timeout 200 python tools/bench_configs.py 3 2> gpurun_out/cfg3_$name.err | sed "s/^/$name /"
+  fi
 done
