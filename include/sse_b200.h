@@ -175,7 +175,14 @@ int sse_halo_unpack_aux(sse_handle* h);
  * already queued, on the handle's copy stream; sse_sync_copies waits for the copies. */
 int sse_upload_and_nodal_values(sse_handle* h, const double* u_host);
 int sse_download_dudt_range(sse_handle* h, double* dudt_host, int64_t k_begin, int64_t k_end);
+/* H2D of the element range [k_begin, k_end) of u_host (base of the whole local array) on the copy
+ * stream + loop A of that range once it has landed; first != 0 on the first range of a residual
+ * (orders the copies after the previous residual's readers of u). */
+int sse_upload_range_and_nodal_values(sse_handle* h, const double* u_host, int64_t k_begin,
+                                      int64_t k_end, int first);
 int sse_sync_copies(sse_handle* h);
+/* split != 0: sse_download_dudt_range copies on a second copy stream (full-duplex with uploads) */
+int sse_set_copy_streams(sse_handle* h, int split);
 /* Asynchronous (stream-ordered) H2D of the state / D2H of dudt (the latter synchronises). */
 int sse_upload_state(sse_handle* h, const double* u_host);
 int sse_download_dudt(sse_handle* h, double* dudt_host);

@@ -91,6 +91,7 @@ struct sse_handle {
   double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
   double* erk_u = nullptr;      //               stage state
   int erk_stages = 0;
+  int split_copy_streams = 0;   // 1: sse_download_dudt_range copies on d2h_stream (sse_set_copy_streams)
   int b_stages = 3;   // second order: bit 0 = auxiliary_variable! (A2), bit 1 = time_derivative!
   int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
   size_t smem_a = 0, smem_b = 0;
@@ -1092,6 +1093,35 @@ int sse_upload_and_nodal_values(sse_handle* h, const double* u_host) {
   return rc;
 }
 
+// The same for one element range [k_begin, k_end) of the shard (u_host is the base of the whole
+// local array): H2D on the copy stream, loop A of the range on the main stream once it has
+// landed.  Lets the host framework choose the upload order (boundary elements first, so that the
+// halo exchange starts early) and interleave loop B of ranges whose neighbours are in place.
+int sse_upload_range_and_nodal_values(sse_handle* h, const double* u_host, int64_t k_begin,
+                                      int64_t k_end, int first) {
+  if (!h || !u_host) return fail("null argument");
+  if (k_begin < 0 || k_end > h->cfg.N_e || k_begin > k_end) return fail("bad element range");
+  if (k_begin == k_end) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
+  if (first) {   // the copy stream must not overwrite u while earlier main-stream work reads it
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev[3], 0));
+  }
+  cudaEvent_t ev = h->ev_chunk[h->next_ev++ % SSE_MAX_CHUNKS];
+  CU(cudaMemcpyAsync(h->u + k_begin * blk, u_host + k_begin * blk,
+                     (k_end - k_begin) * blk * sizeof(double), cudaMemcpyHostToDevice,
+                     h->copy_stream));
+  CU(cudaEventRecord(ev, h->copy_stream));
+  CU(cudaStreamWaitEvent(h->stream, ev, 0));
+  h->G.k_begin = k_begin;
+  h->G.N_e = k_end;
+  int rc = run_a(h, h->u);
+  h->G.k_begin = 0;
+  h->G.N_e = h->cfg.N_e;
+  return rc;
+}
+
 // ... and D2H of dudt for the element range [k_begin, k_end), ordered after the work already
 // queued on the main stream, on the copy stream (sse_sync_copies waits for all of them).
 int sse_download_dudt_range(sse_handle* h, double* dudt_host, int64_t k_begin, int64_t k_end) {
@@ -1101,11 +1131,11 @@ int sse_download_dudt_range(sse_handle* h, double* dudt_host, int64_t k_begin, i
   CU(cudaSetDevice(h->cfg.device));
   const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
   cudaEvent_t ev = h->ev_chunk[h->next_ev++ % SSE_MAX_CHUNKS];
+  cudaStream_t cs = h->split_copy_streams ? h->d2h_stream : h->copy_stream;
   CU(cudaEventRecord(ev, h->stream));
-  CU(cudaStreamWaitEvent(h->copy_stream, ev, 0));
+  CU(cudaStreamWaitEvent(cs, ev, 0));
   CU(cudaMemcpyAsync(dudt_host + k_begin * blk, h->dudt + k_begin * blk,
-                     (k_end - k_begin) * blk * sizeof(double), cudaMemcpyDeviceToHost,
-                     h->copy_stream));
+                     (k_end - k_begin) * blk * sizeof(double), cudaMemcpyDeviceToHost, cs));
   return 0;
 }
 
@@ -1113,6 +1143,18 @@ int sse_sync_copies(sse_handle* h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->copy_stream));
+  if (h->split_copy_streams) CU(cudaStreamSynchronize(h->d2h_stream));
+  return 0;
+}
+
+// 1: range downloads use the second copy stream, so that a D2H waiting for its loop B does not
+// hold back the H2D of later ranges queued behind it (the interleaved host-buffer flow)
+int sse_set_copy_streams(sse_handle* h, int split) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->copy_stream));
+  CU(cudaStreamSynchronize(h->d2h_stream));
+  h->split_copy_streams = split ? 1 : 0;
   return 0;
 }
 

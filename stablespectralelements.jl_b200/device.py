@@ -73,7 +73,8 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_download_dudt_range", "sse_sync_copies", "sse_functional",
            "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host",
            "sse_auxiliary_variable_range", "sse_time_derivative_only_range",
-           "sse_halo_pack_aux", "sse_halo_unpack_aux", "sse_erk_step"]
+           "sse_halo_pack_aux", "sse_halo_unpack_aux", "sse_erk_step",
+           "sse_upload_range_and_nodal_values", "sse_set_copy_streams"]
 
 
 def load_library(path: Optional[str] = None, allow_emulation: bool = False):
@@ -135,6 +136,8 @@ def load_library(path: Optional[str] = None, allow_emulation: bool = False):
     lib.sse_halo_pack_aux.argtypes = [vp]
     lib.sse_halo_unpack_aux.argtypes = [vp]
     lib.sse_erk_step.argtypes = [vp, C.c_int, c_d_p, c_d_p, C.c_double]
+    lib.sse_upload_range_and_nodal_values.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int]
+    lib.sse_set_copy_streams.argtypes = [vp, C.c_int]
     if path is None:
         _LIB = lib
     return lib
@@ -384,6 +387,16 @@ class DeviceResidual:
         assert u.shape == self.shape and u.dtype == np.float64 and u.flags.c_contiguous
         self._check(self.lib.sse_upload_and_nodal_values(self.h, u.ctypes.data),
                     "sse_upload_and_nodal_values")
+
+    def upload_range_and_nodal_values(self, u: np.ndarray, k_begin: int, k_end: int,
+                                      first: bool = False):
+        assert u.shape == self.shape and u.dtype == np.float64 and u.flags.c_contiguous
+        self._check(self.lib.sse_upload_range_and_nodal_values(self.h, u.ctypes.data, k_begin,
+                                                               k_end, int(first)),
+                    "sse_upload_range_and_nodal_values")
+
+    def set_copy_streams(self, split: bool):
+        self._check(self.lib.sse_set_copy_streams(self.h, int(split)), "sse_set_copy_streams")
 
     def download_dudt_range(self, dudt: np.ndarray, k_begin: int, k_end: int):
         assert dudt.shape == self.shape and dudt.dtype == np.float64 and dudt.flags.c_contiguous

@@ -232,10 +232,77 @@ class DistributedResidual:
         d.halo_unpack_aux()
         loop_b(boundary, d.time_derivative_only_range)
 
+    def _neighbour_span(self):
+        """Per local element: lowest / highest LOCAL element one of its facet nodes reads from
+        (halo reads excluded) -- what has to have run loop A before loop B of the element may."""
+        if getattr(self, "_span", None) is None:
+            N_f, n_loc = self.part.mapP_local.shape
+            kk = self.part.mapP_local // N_f
+            own = np.arange(n_loc)[None, :]
+            local = kk < n_loc
+            lo = np.where(local, kk, own).min(axis=0)
+            hi = np.where(local, kk, own).max(axis=0)
+            self._span = (np.minimum(lo, own[0]), np.maximum(hi, own[0]))
+        return self._span
+
+    def _flow_host_interleaved(self, u_host, dudt_host, n_pieces: int = 12,
+                               min_piece: int = 2048):
+        """Host-buffer residual of a first-order equation with the upload interleaved with BOTH
+        loops (opt-in, SSE_B200_SHARD_PIPELINE=1; same generator protocol as ``_flow``).
+
+        The default host path uploads everything (overlapped with loop A only) before loop B
+        starts, so it costs H2D + loop B.  Here the boundary elements go first -- their traces
+        are packed and the halo exchange starts while the interior is still being uploaded --
+        then the interior arrives piece by piece, and loop B of a piece is launched as soon as
+        loop A has been queued for every element it reads a trace from; results stream back on
+        the second copy stream.  All kernels still run on ONE stream in program order; the only
+        asynchrony is the existing H2D-event -> loop A and loop B -> event -> D2H pattern."""
+        d = self.dev
+        N = d.N_e
+        k_lo, k_hi = self.part.interior
+        boundary = [(a, b) for a, b in ((0, k_lo), (max(k_hi, k_lo), N)) if b > a]
+        n_pieces = max(1, min(n_pieces, (k_hi - k_lo) // min_piece)) if k_hi > k_lo else 0
+        cuts = [k_lo + ((k_hi - k_lo) * q) // n_pieces for q in range(n_pieces + 1)] if n_pieces else []
+        interior = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        span_lo, span_hi = self._neighbour_span()
+        need = [(int(span_lo[a:b].min()), int(span_hi[a:b].max()) + 1) for a, b in interior]
+        have = np.zeros(N, dtype=bool)                 # loop A queued for these elements
+
+        first = True
+        for a, b in boundary:
+            d.upload_range_and_nodal_values(u_host, a, b, first=first)
+            first = False
+            have[a:b] = True
+        d.halo_pack()
+        wait = yield d.N_c
+        done = [False] * len(interior)
+        for i, (a, b) in enumerate(interior):
+            d.upload_range_and_nodal_values(u_host, a, b, first=first)
+            first = False
+            have[a:b] = True
+            for j, (c, e) in enumerate(interior[:i + 1]):
+                if not done[j] and have[need[j][0]:need[j][1]].all():
+                    d.time_derivative_range(c, e)
+                    d.download_dudt_range(dudt_host, c, e)
+                    done[j] = True
+        for j, (c, e) in enumerate(interior):          # whatever is still open (normally none)
+            if not done[j]:
+                assert have[need[j][0]:need[j][1]].all()
+                d.time_derivative_range(c, e)
+                d.download_dudt_range(dudt_host, c, e)
+        wait()
+        d.halo_unpack()
+        for a, b in boundary:
+            d.time_derivative_range(a, b)
+            d.download_dudt_range(dudt_host, a, b)
+
     def _exchange_and_time_derivative(self, dudt_host=None):
         """Halo exchange(s) over NCCL + the loops that follow loop A."""
+        self._drive(self._flow(dudt_host))
+
+    def _drive(self, flow):
+        """Run a flow generator with NCCL as the transport of its halo exchanges."""
         import torch.distributed as dist
-        flow = self._flow(dudt_host)
         try:
             width = next(flow)
             while True:
@@ -258,8 +325,16 @@ class DistributedResidual:
         if self.world == 1:
             self.dev.residual_host(u, dudt)
             return
-        self.dev.upload_and_nodal_values(u)          # chunked H2D overlapped with loop A
-        self._exchange_and_time_derivative(dudt)     # loop B overlapped with the D2H copies
+        import os
+        if os.environ.get("SSE_B200_SHARD_PIPELINE") == "1" and not self.second_order:
+            # opt-in: upload interleaved with both loops (see _flow_host_interleaved)
+            if not getattr(self, "_split_streams", False):
+                self.dev.set_copy_streams(True)
+                self._split_streams = True
+            self._drive(self._flow_host_interleaved(u, dudt))
+        else:
+            self.dev.upload_and_nodal_values(u)          # chunked H2D overlapped with loop A
+            self._exchange_and_time_derivative(dudt)     # loop B overlapped with the D2H copies
         self.dev.sync_copies()
 
     def timed_residuals(self, steps: int) -> float:

@@ -282,3 +282,56 @@ def test_tuning_knob_variants_in_emulation(defines):
                 d.close()
     finally:
         dev._LIB = saved
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_interleaved_host_flow_in_emulation(emu_lib, world):
+    """DistributedResidual._flow_host_interleaved (opt-in SSE_B200_SHARD_PIPELINE=1): boundary
+    elements uploaded first, interior pieces uploaded / loop A / loop B as their neighbours
+    arrive.  The logical order of the launches is what the emulator checks (it executes them in
+    program order, as the single compute stream does); result = the single-handle residual."""
+    Shard = _emu_shard_class()
+    # a mesh that is long in the sharded direction, so that each shard has a real interior
+    import math
+    from sse_b200.conservation_laws import EulerEquations, LaxFriedrichsNumericalFlux
+    from sse_b200.geometric_factors import ChanWilcoxMetrics, make_spatial_discretization
+    from sse_b200.grid_functions import EulerPeriodicTest
+    from sse_b200.mesh import ChanWarping, uniform_periodic_mesh, warp_mesh
+    from sse_b200.reference_approximation import ModalTensor, Tet, make_reference_approximation
+    from sse_b200.solvers import (FluxDifferencingForm, ReferenceOperator, Solver,
+                                  project_function)
+    L = 2 * math.pi
+    ra = make_reference_approximation(ModalTensor(2), Tet(), mapping_degree=2)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, L),) * 3, (2, 2, 6 * world)), ra,
+                     ChanWarping(1 / 16, (L, L, L)))
+    sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
+    solver = Solver(EulerEquations(3, 1.4), sd,
+                    FluxDifferencingForm(inviscid_numerical_flux=LaxFriedrichsNumericalFlux()),
+                    ReferenceOperator(), lazy=True)
+    u0 = project_function(EulerPeriodicTest(3, 1.4, 0.2, L), sd)
+    u = cases.rough_state(solver, u0, seed=6)
+    whole = dev.DeviceResidual(solver)
+    try:
+        ref = np.empty_like(u)
+        whole.residual_host(u, ref)
+    finally:
+        whole.close()
+    shards = [Shard(solver, rank=r, world=world, device=0) for r in range(world)]
+    try:
+        import test_gpu_sharded_emulation as ts
+        us = [np.ascontiguousarray(u[sh.elements]) for sh in shards]
+        outs = [np.full_like(x, np.nan) for x in us]
+        flows = [sh._flow_host_interleaved(x, o, n_pieces=5, min_piece=6)
+                 for sh, x, o in zip(shards, us, outs)]
+        widths = [next(f) for f in flows]
+        ts._local_exchange(shards, widths[0])
+        for f in flows:
+            with pytest.raises(StopIteration):
+                f.send(lambda: None)
+        for sh in shards:
+            sh.dev.sync_copies()
+            assert sh.part.interior[1] - sh.part.interior[0] >= 30   # several pieces were used
+        assert np.array_equal(np.concatenate(outs, axis=0), ref)
+    finally:
+        for sh in shards:
+            sh.close()
