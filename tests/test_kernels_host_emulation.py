@@ -335,3 +335,51 @@ def test_interleaved_host_flow_in_emulation(emu_lib, world):
     finally:
         for sh in shards:
             sh.close()
+
+
+def _quad_euler(p):
+    from sse_b200.conservation_laws import EulerEquations, LaxFriedrichsNumericalFlux
+    from sse_b200.geometric_factors import make_spatial_discretization
+    from sse_b200.grid_functions import IsentropicVortex
+    from sse_b200.mesh import uniform_periodic_mesh, warp_mesh
+    from sse_b200.reference_approximation import NodalTensor, Quad, make_reference_approximation
+    from sse_b200.solvers import FluxDifferencingForm, ReferenceOperator, Solver, project_function
+    ra = make_reference_approximation(NodalTensor(p), Quad(), mapping_degree=p)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (3, 3)), ra, 0.1)
+    sd = make_spatial_discretization(mesh, ra)
+    form = FluxDifferencingForm(inviscid_numerical_flux=LaxFriedrichsNumericalFlux())
+    solver = Solver(EulerEquations(2, 1.4), sd, form, ReferenceOperator(), lazy=True)
+    ic = IsentropicVortex(gamma=1.4, Ma=0.4, theta=0.0, R=0.1, beta=0.5, x_0=(0.5, 0.5))
+    return solver, project_function(ic, sd)
+
+
+SWEEP = {   # degrees and element types outside the specialised kernels' range (generic kernels)
+    "euler_tet_p5": lambda: cases.euler_tet_case(p=5, M=2, lazy=True, warp=True, ic="periodic"),
+    "euler_tet_p1": lambda: cases.euler_tet_case(p=1, M=2, lazy=True, warp=True, ic="periodic"),
+    "euler_tri_p6": lambda: cases.euler_tri_case(p=6, M=2, lazy=True),
+    "euler_tri_p5_nodal_ec": lambda: cases.euler_tri_case(p=5, M=2, lazy=True, approx="nodal",
+                                                          interface="ec"),
+    "adv_tet_p5": lambda: cases.advection_tet_case(p=5, M=2, lazy=True),
+    "adv_tet_p1": lambda: cases.advection_tet_case(p=1, M=2, lazy=True),
+    "adv_tri_p7": lambda: cases.advection_tri_case(p=7, M=2, lazy=True),
+    "hex_p5_ec": lambda: cases.euler_hex_case(p=5, M=2, lazy=True),
+    "hex_p2_lf": lambda: cases.euler_hex_case(p=2, M=2, lazy=True, interface="lf"),
+    "quad_euler_p4": lambda: _quad_euler(4),
+    "advdiff2d_p5": lambda: cases.advection_diffusion_case(d=2, p=5, M=2, lazy=True),
+    "advdiff1d_p2": lambda: cases.advection_diffusion_case(d=1, p=2, M=3, lazy=True),
+    "burgers_tri_p5": lambda: cases.burgers_tri_case(p=5, M=2, lazy=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SWEEP))
+def test_degree_and_element_sweep_in_emulation(emu_lib, name):
+    solver, u0 = SWEEP[name]()
+    u = cases.rough_state(solver, u0, seed=1)
+    d = dev.DeviceResidual(solver)
+    try:
+        dudt = np.full_like(u, np.nan)
+        d.residual_host(u, dudt)
+        ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+        assert _rel(dudt, ref) < 1e-12
+    finally:
+        d.close()
