@@ -588,12 +588,22 @@ struct FDCfg {
     return xmax(oEnd, oM + ev(EL * NC * Np));
   }
   static __host__ __device__ constexpr size_t bytes(int Np) { return sizeof(double) * (size_t)(oX(Np) + sX); }
+  // volume-only kernel: state / metric staging + the pair-exchange buffers
+  static __host__ __device__ constexpr size_t bytes_volume() {
+    return sizeof(double) * (size_t)(oSf + NBUF * H * NC * nq);
+  }
 };
 
-template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
-__global__ void __launch_bounds__(128, SSE_FD_MINB)
-k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
-                  const double* __restrict__ u_f, double* __restrict__ dudt) {
+// PART selects what the body does: 0 = the whole of loop B (the default, one fused kernel);
+// 1 = volume flux differencing only, nodal residual written to r_q; 2 = everything else (interface
+// flux, facet correction, lift, projection, mass solve, epilogue), nodal residual read from r_q.
+// The split pair exists so that the volume kernel can run under its own register / shared-memory
+// budget and be measured against the FP64 roofline on its own (opt-in, SSE_B200_SPLIT_B=1).
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC, int PART>
+__device__ __forceinline__ void fluxdiff_tensor_body(
+    const FastTables& F, const Tables& T, const Geo& G, const Phys& P, const RK& rk,
+    const double* __restrict__ u_q, const double* __restrict__ u_f, double* __restrict__ dudt,
+    double* __restrict__ r_q) {
   using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
   constexpr int NC = Cf::NC, NS2 = Cf::NS2, NQ = Cf::NQ, NF = Cf::NF;
   constexpr int DD = DIM * DIM, H = Cf::H, KH = Cf::KH, EL = Cf::EL, nq = Cf::nq, nf = Cf::nf;
@@ -607,7 +617,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   double* sFf = sm + Cf::oFf;
   double* sR = sm + Cf::oR;
   double* sM = sm + Cf::oM;
-  double* sX = sm + Cf::oX(Np);
+  double* sX = sm + (PART == 1 ? Cf::oSf : Cf::oX(Np));
   const long long k0 = G.k_begin + (long long)blockIdx.x * EL;
   const int tid = threadIdx.x;
   const bool active = tid < nq;
@@ -626,11 +636,14 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
       };
       pf(u_q + kp * NC * NQ, EL * NC * NQ * 8);
       pf(G.L_q + kp * DD * NQ, EL * DD * NQ * 8);
-      pf(G.nJf + kp * NF * DIM, EL * NF * DIM * 8);
-      pf(u_f + kp * NC * NF, EL * NC * NF * 8);
-      pf(G.J_f + kp * NF, EL * NF * 8);
-      pf(G.toff + kp * NF, EL * NF * 4);
-      pf(G.J_q + kp * NQ, EL * NQ * 8);
+      if constexpr (PART != 1) {
+        pf(G.nJf + kp * NF * DIM, EL * NF * DIM * 8);
+        pf(u_f + kp * NC * NF, EL * NC * NF * 8);
+        pf(G.J_f + kp * NF, EL * NF * 8);
+        pf(G.toff + kp * NF, EL * NF * 4);
+        pf(G.J_q + kp * NQ, EL * NQ * 8);
+      }
+      if constexpr (PART == 2) pf(r_q + kp * NC * NQ, EL * NC * NQ * 8);
     }
   }
   double si[2 * NS2], Li[DD], r[NC];
@@ -642,7 +655,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phases 0/1.  All global loads of the CTA's first round are issued before any
   // arithmetic so the DRAM round trips of the volume data (u_q, Λ_q) and of the facet data
   // (J_f, nJf, own trace, exterior offset -> exterior trace) overlap.
-  const bool hasf = tid < nf;
+  const bool hasf = (PART != 1) && tid < nf;
   const int fj = hasf ? tid % NF : 0, fe = hasf ? tid / NF : 0;
   const long long fk = min(k0 + fe, G.N_e - 1);
   const long long fgj = fk * NF + fj;
@@ -668,19 +681,28 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 #pragma unroll
     for (int c = 0; c < NC; ++c) fup[c] = __ldcg(u_f + fext + (long long)c * NF);
   }
+  if constexpr (PART == 2) {   // the volume kernel's nodal residual
+    if (active) {
+      long long k = min(k0 + e, G.N_e - 1);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r[c] = __ldcg(r_q + (k * NC + c) * NQ + i);
+    }
+  }
   // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
   if (active) {
     cons_to_state<DIM, LAW>(P, uu0, si);
+    if constexpr (PART != 2) {   // other nodes' states are only read by the volume term
 #pragma unroll
-    for (int c = 0; c < NS2; ++c) sS2[c * nq + tid] = make_double2(si[2 * c], si[2 * c + 1]);
+      for (int c = 0; c < NS2; ++c) sS2[c * nq + tid] = make_double2(si[2 * c], si[2 * c + 1]);
 #pragma unroll
-    for (int m = 0; m < DIM; ++m) {
-      sLa[m * nq + tid] = make_double2(Li[m], Li[m + DIM]);
-      if constexpr (DIM == 3) sLb[m * nq + tid] = Li[m + 2 * DIM];
+      for (int m = 0; m < DIM; ++m) {
+        sLa[m * nq + tid] = make_double2(Li[m], Li[m + DIM]);
+        if constexpr (DIM == 3) sLb[m * nq + tid] = Li[m + 2 * DIM];
+      }
     }
   }
   // ---- phase 1: interface numerical flux at the facet nodes
-  for (int idx = tid; idx < nf; idx += 128) {
+  for (int idx = tid; idx < (PART == 1 ? 0 : nf); idx += 128) {
     const int j = idx % NF, ee = idx / NF;
     double nJ[DIM], nfv[DIM], sl[2 * NS2], fs[NC];
 #pragma unroll
@@ -718,7 +740,7 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 
   // ---- phase 2: volume flux differencing, every pair on a tensor line evaluated once
 #pragma unroll
-  for (int l = 0; l < DIM; ++l) {
+  for (int l = 0; l < (PART == 2 ? 0 : DIM); ++l) {
     constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
     const int stride = (l == 0) ? s0 : (l == 1 ? s1 : 1);
     const int al = (i / stride) % N1;
@@ -782,6 +804,13 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     }
   }
 
+  if constexpr (PART == 1) {
+    if (active && k0 + e < G.N_e) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) r_q[((k0 + e) * NC + c) * NQ + i] = r[c];
+    }
+    return;
+  }
   // ---- phases 3/4: facet correction (ELL rows of C = R^T B), exchanged in two halves
   if (!T.r_is_selection) {
 #pragma unroll
@@ -905,6 +934,32 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // ---- phase 6: dudt = M^-1 V^T r_q
   project_and_solve_t<DIM, N1, NC, EL>(T, G, k0, sR, sM, sX);
   store_result(T, G, rk, k0, EL, NC, sM, dudt);
+}
+
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(128, SSE_FD_MINB)
+k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
+                  const double* __restrict__ u_f, double* __restrict__ dudt) {
+  fluxdiff_tensor_body<DIM, N1, LAW, COLLAPSED, KC, 0>(F, T, G, P, rk, u_q, u_f, dudt, nullptr);
+}
+
+// The split pair (opt-in): volume term under its own occupancy target, then the rest.
+#ifndef SSE_FD_VOL_MINB
+#define SSE_FD_VOL_MINB 6
+#endif
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(128, SSE_FD_VOL_MINB)
+k_fluxdiff_volume(FastTables F, Tables T, Geo G, Phys P, const double* __restrict__ u_q,
+                  double* __restrict__ r_q) {
+  fluxdiff_tensor_body<DIM, N1, LAW, COLLAPSED, KC, 1>(F, T, G, P, RK{}, u_q, nullptr, nullptr,
+                                                       r_q);
+}
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(128, SSE_FD_MINB)
+k_fluxdiff_facet(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
+                 const double* __restrict__ u_f, double* __restrict__ dudt,
+                 double* __restrict__ r_q) {
+  fluxdiff_tensor_body<DIM, N1, LAW, COLLAPSED, KC, 2>(F, T, G, P, rk, u_q, u_f, dudt, r_q);
 }
 
 // ============================================ loop B, standard form, reference operators

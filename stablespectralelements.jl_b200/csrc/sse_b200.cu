@@ -91,6 +91,8 @@ struct sse_handle {
   double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
   double* erk_u = nullptr;      //               stage state
   int erk_stages = 0;
+  int split_b = 0;              // 1: loop B as k_fluxdiff_volume + k_fluxdiff_facet (SSE_B200_SPLIT_B=1)
+  double* r_q = nullptr;        //    nodal residual handed from the volume to the facet kernel
   int split_copy_streams = 0;   // 1: sse_download_dudt_range copies on d2h_stream (sse_set_copy_streams)
   int b_stages = 3;   // second order: bit 0 = auxiliary_variable! (A2), bit 1 = time_derivative!
   int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
@@ -283,6 +285,22 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
     if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
     const char* e = getenv("SSE_B200_PREFETCH");
     h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_FD_MINB * Cf::EL;
+  }
+  if (h->split_b) {
+    const size_t smem_v = Cf::bytes_volume();
+    CU(cudaFuncSetAttribute(k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+    CU(cudaFuncSetAttribute(k_fluxdiff_facet<DIM, N1, LAW, COLLAPSED, KC>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Geo Gv = h->G;
+    if (Gv.pf_dist) Gv.pf_dist = Gv.pf_dist / SSE_FD_MINB * SSE_FD_VOL_MINB;
+    k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem_v, h->stream)(
+        h->F, h->T, Gv, h->P, h->u_q, h->r_q);
+    k_fluxdiff_facet<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
+        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->r_q);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
   }
   k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
@@ -941,6 +959,13 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
+    {   // opt-in: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
+      const char* e = getenv("SSE_B200_SPLIT_B");
+      if (h->fast_b && e && atoi(e) == 1) {
+        if (dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->r_q)) return -1;
+        h->split_b = 1;
+      }
+    }
     if (h->fast_std && !force_generic && law_t == LAW_ADV && h->collapsed && h->n1 >= 3 &&
         h->n1 <= 5 && cfg->strategy == SSE_REFERENCE_OPERATOR &&
         d == 3 && h->kc == 3 + h->n1)

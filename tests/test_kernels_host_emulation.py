@@ -383,3 +383,42 @@ def test_degree_and_element_sweep_in_emulation(emu_lib, name):
         assert _rel(dudt, ref) < 1e-12
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("name", ["euler3d_tet_p4_warp_lf", "euler3d_tet_p3_warp_ec",
+                                  "euler2d_tri_p4_lf"])
+def test_split_loop_b_in_emulation(emu_lib, name, monkeypatch):
+    """Opt-in SSE_B200_SPLIT_B=1: loop B as k_fluxdiff_volume (volume flux differencing under its
+    own occupancy target, nodal residual to global memory) + k_fluxdiff_facet (everything else).
+    Same arithmetic per node as the fused kernel, so the result must be BITWISE the fused one."""
+    build, _ = CASES[name]
+    solver, u0 = build()
+    u = cases.rough_state(solver, u0, seed=3)
+    outs = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("SSE_B200_SPLIT_B", split)
+        d = dev.DeviceResidual(solver)
+        try:
+            emu_lib.emu_launch_log()
+            dudt = np.full_like(u, np.nan)
+            d.residual_host(u, dudt)
+            log = emu_lib.emu_launch_log().decode()
+            assert ("k_fluxdiff_volume" in log) == (split == "1")
+            assert ("k_fluxdiff_facet" in log) == (split == "1")
+            outs[split] = dudt
+        finally:
+            d.close()
+    ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+    assert _rel(outs["1"], ref) < 1e-12
+    assert np.array_equal(outs["0"], outs["1"])
+    # race check of the split kernels (descending thread order inside every barrier interval)
+    monkeypatch.setenv("SSE_B200_SPLIT_B", "1")
+    d = dev.DeviceResidual(solver)
+    try:
+        emu_lib.emu_set_order(1)
+        dudt = np.full_like(u, np.nan)
+        d.residual_host(u, dudt)
+        assert np.array_equal(dudt, outs["1"])
+    finally:
+        emu_lib.emu_set_order(0)
+        d.close()
