@@ -1,0 +1,95 @@
+"""Opt-in variants that were written and checked on the host emulator after the round's GPU
+budget was spent: their first run on real hardware is this file, which
+sorts last among the GPU tests on purpose.
+
+* SSE_B200_SPLIT_B=1: loop B as k_fluxdiff_volume + k_fluxdiff_facet -- must be BITWISE the fused
+  kernel (same per-node arithmetic, the nodal residual merely travels through global memory).
+* DistributedResidual._flow_host_interleaved: host-buffer residual of a shard with the upload
+  interleaved with both loops; exercised here with two shards on one GPU (device copies as the
+  halo transport), which is what checks its stream / event dependencies on real hardware."""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("p", [4, 3])
+def test_split_loop_b_is_bitwise_the_fused_kernel(p, monkeypatch):
+    from sse_b200 import device as dev
+    solver, u0 = cases.euler_tet_case(p=p, M=4, lazy=True, warp=True, ic="periodic")
+    u = cases.rough_state(solver, u0, seed=3)
+    outs = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("SSE_B200_SPLIT_B", split)
+        d = dev.DeviceResidual(solver)
+        try:
+            dudt = np.full_like(u, np.nan)
+            for _ in range(2):
+                d.residual_host(u, dudt)
+            outs[split] = dudt
+            launches = d.kernel_launches()
+        finally:
+            d.close()
+    assert np.all(np.isfinite(outs["1"]))
+    assert np.array_equal(outs["0"], outs["1"])
+
+
+def _long_mesh_case(n_layers):
+    from sse_b200.conservation_laws import EulerEquations, LaxFriedrichsNumericalFlux
+    from sse_b200.geometric_factors import ChanWilcoxMetrics, make_spatial_discretization
+    from sse_b200.grid_functions import EulerPeriodicTest
+    from sse_b200.mesh import ChanWarping, uniform_periodic_mesh, warp_mesh
+    from sse_b200.reference_approximation import ModalTensor, Tet, make_reference_approximation
+    from sse_b200.solvers import (FluxDifferencingForm, ReferenceOperator, Solver,
+                                  project_function)
+    L = 2 * math.pi
+    ra = make_reference_approximation(ModalTensor(3), Tet(), mapping_degree=2)
+    mesh = warp_mesh(uniform_periodic_mesh(ra, ((0.0, L),) * 3, (6, 6, n_layers)), ra,
+                     ChanWarping(1 / 16, (L, L, L)))
+    sd = make_spatial_discretization(mesh, ra, ChanWilcoxMetrics())
+    solver = Solver(EulerEquations(3, 1.4), sd,
+                    FluxDifferencingForm(inviscid_numerical_flux=LaxFriedrichsNumericalFlux()),
+                    ReferenceOperator(), lazy=True)
+    return solver, project_function(EulerPeriodicTest(3, 1.4, 0.2, L), sd)
+
+
+def test_interleaved_host_flow_two_shards_on_one_gpu():
+    import torch
+    from sse_b200 import device as dev
+    from sse_b200.distributed import DistributedResidual
+    from test_gpu_sharded_emulation import _local_exchange
+    solver, u0 = _long_mesh_case(24)                      # 5184 elements, 2592 per shard
+    u = cases.rough_state(solver, u0, seed=6)
+    whole = dev.DeviceResidual(solver)
+    try:
+        ref = np.empty_like(u)
+        whole.residual_host(u, ref)
+    finally:
+        whole.close()
+    shards = [DistributedResidual(solver, rank=r, world=2, device=0) for r in range(2)]
+    try:
+        for sh in shards:
+            sh.dev.set_copy_streams(True)
+        pin = lambda a: torch.from_numpy(a.copy()).pin_memory().numpy()
+        us = [pin(np.ascontiguousarray(u[sh.elements])) for sh in shards]
+        outs = [pin(np.full_like(x, np.nan)) for x in us]
+        for rep in range(3):                              # back-to-back calls reuse the buffers
+            for o in outs:
+                o[...] = np.nan
+            flows = [sh._flow_host_interleaved(x, o, n_pieces=6, min_piece=200)
+                     for sh, x, o in zip(shards, us, outs)]
+            widths = [next(f) for f in flows]
+            _local_exchange(shards, widths[0])
+            for f in flows:
+                with pytest.raises(StopIteration):
+                    f.send(lambda: None)
+            for sh in shards:
+                sh.dev.sync_copies()
+            assert np.array_equal(np.concatenate(outs, axis=0), ref), rep
+    finally:
+        for sh in shards:
+            sh.close()
