@@ -2,8 +2,9 @@
 budget was spent: their first run on real hardware is this file, which
 sorts last among the GPU tests on purpose.
 
-* SSE_B200_SPLIT_B=1: loop B as k_fluxdiff_volume + k_fluxdiff_facet -- must be BITWISE the fused
-  kernel (same per-node arithmetic, the nodal residual merely travels through global memory).
+* SSE_B200_SPLIT_B=1: loop B as k_fluxdiff_volume + k_fluxdiff_facet -- must reproduce the fused
+  kernel to round-off (same per-node arithmetic, the nodal residual merely travels through
+  global memory).
 * DistributedResidual._flow_host_interleaved: host-buffer residual of a shard with the upload
   interleaved with both loops; exercised here with two shards on one GPU (device copies as the
   halo transport), which is what checks its stream / event dependencies on real hardware."""
@@ -18,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("p", [4, 3])
-def test_split_loop_b_is_bitwise_the_fused_kernel(p, monkeypatch):
+def test_split_loop_b_matches_the_fused_kernel(p, monkeypatch):
     from sse_b200 import device as dev
     solver, u0 = cases.euler_tet_case(p=p, M=4, lazy=True, warp=True, ic="periodic")
     u = cases.rough_state(solver, u0, seed=3)
@@ -35,7 +36,10 @@ def test_split_loop_b_is_bitwise_the_fused_kernel(p, monkeypatch):
         finally:
             d.close()
     assert np.all(np.isfinite(outs["1"]))
-    assert np.array_equal(outs["0"], outs["1"])
+    # same per-node arithmetic in the same order; nvcc may still contract multiply-adds
+    # differently in the two instantiations, hence round-off rather than bitwise here (the
+    # emulator build, which contracts nothing, is bitwise: test_kernels_host_emulation.py)
+    assert np.max(np.abs(outs["0"] - outs["1"])) <= 1e-13 * np.max(np.abs(outs["0"]))
 
 
 def _long_mesh_case(n_layers):
