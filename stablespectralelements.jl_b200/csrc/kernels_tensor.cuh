@@ -556,6 +556,9 @@ k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restric
 #ifndef SSE_FD_SINGLE_BUF
 #define SSE_FD_SINGLE_BUF 0
 #endif
+#ifndef SSE_STD_HOIST
+#define SSE_STD_HOIST 0      // k_standard_tensor: facet / Jacobian loads hoisted into the prologue
+#endif
 
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
 struct FDCfg {
@@ -1015,6 +1018,24 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // 44 independent loads per thread in flight and the extra requests only compete with them.)
   for (int idx = tid; idx < DIM * N1 * N1; idx += 128) sD[idx] = __ldg(F.D1 + idx);
 
+#if SSE_STD_HOIST
+  // Variant (-DSSE_STD_HOIST=1): the facet data of the first round of phase 1 and the Jacobians
+  // of phase 3 are requested here, together with the volume data, so that a batch pays one DRAM
+  // round trip (+ the dependent exterior-trace gather) instead of four in a row.
+  const bool hfac = tid < NB * NF;            // this thread owns a facet node in the first round
+  const int hj = hfac ? tid % NF : 0, hb = hfac ? tid / NF : 0;
+  const long long hk = min(k0 + hb, G.N_e - 1);
+  const long long hgj = hk * NF + hj;
+  const double hJf = __ldcg(G.J_f + hgj);
+  const int hext = __ldcg(G.toff + hgj);
+  double hnJ[DIM], hum[1], hup[1], jq[NB];
+#pragma unroll
+  for (int m = 0; m < DIM; ++m) hnJ[m] = __ldcg(G.nJf + hgj * DIM + m);
+  hum[0] = __ldcg(u_f + hk * NF + hj);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) jq[b] = active ? __ldcg(G.J_q + min(k0 + b, G.N_e - 1) * NQ + i) : 1.0;
+#endif
+
   double ha[NB][DIM];
   // ---- phase 0: φ(u) and the metric scalars h_m at the volume nodes
   if (active) {
@@ -1026,6 +1047,9 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 #pragma unroll
       for (int c = 0; c < DD; ++c) Lq[b][c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
     }
+#if SSE_STD_HOIST
+    hup[0] = __ldcg(u_f + hext);     // dependent on toff: issued behind the volume loads
+#endif
     const double hw = 0.5 * __ldg(T.W + i);
     double gref[DD];
 #pragma unroll
@@ -1052,6 +1076,9 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
       }
     }
   }
+#if SSE_STD_HOIST
+  if (!active) hup[0] = __ldcg(u_f + hext);
+#endif
   __syncthreads();
   // separable collapsed-face rows of R (see apply_R_t): shared a3-contraction of φ, kept in sR
   // (free until phase 2)
@@ -1073,15 +1100,29 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     const long long k = min(k0 + b, G.N_e - 1);
     const long long gj = k * NF + j;
     double nfv[DIM], sl[2], fs[1];
+#if SSE_STD_HOIST
+    const bool first_round = (idx == tid);
+    const double Jf = first_round ? hJf : __ldcg(G.J_f + gj);
+    const int ext = first_round ? hext : __ldcg(G.toff + gj);
+#else
     const double Jf = __ldcg(G.J_f + gj);
     const int ext = __ldcg(G.toff + gj);
+#endif
     const double iJf = frcp(Jf);
     double an = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) {
+#if SSE_STD_HOIST
+      nfv[m] = (first_round ? hnJ[m] : __ldcg(G.nJf + gj * DIM + m)) * iJf;
+#else
       nfv[m] = __ldcg(G.nJf + gj * DIM + m) * iJf;
+#endif
       an = fma(P.a[m], nfv[m], an);
     }
+#if SSE_STD_HOIST
+    if (first_round) interface_flux_vals<DIM, LAW>(P, 0, hum, hup, nfv, sl, fs);
+    else
+#endif
     interface_flux<DIM, LAW>(P, 0, u_f, k * NF + j, ext, NF, nfv, sl, fs);
     const int rb = __ldg(T.R_rp + j);
     const int desc = __ldg(T.R_desc + j);
@@ -1151,11 +1192,19 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   if (DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
     // M^-1 V^T r = V^T (W/J) (V V^T r): fused V V^T pass, scaling, one V^T
     if constexpr (DIM == 3) apply_VtV_t<N1, NB, 1>(vtab(T), sR, sX);
+#if SSE_STD_HOIST
+    if (active) {
+      const double w = __ldg(T.W + i);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) sR[b * NQ + i] *= fdiv(w, jq[b]);
+    }
+#else
     SSE_LOOP(idx, NB * NQ) {
       const int ii = idx % NQ, b = idx / NQ;
       const long long k = min(k0 + b, G.N_e - 1);
       sR[idx] *= fdiv(__ldg(T.W + ii), __ldcg(G.J_q + k * NQ + ii));
     }
+#endif
     __syncthreads();
     apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
     store_result(T, G, rk, k0, NB, 1, sM, dudt);

@@ -259,7 +259,7 @@ def test_general_explicit_rk_in_emulation(emu_lib):
         solver.close()
 
 
-@pytest.mark.parametrize("defines", [("SSE_STD_NB=2", "SSE_NODAL_NB=4"),
+@pytest.mark.parametrize("defines", [("SSE_STD_NB=2", "SSE_NODAL_NB=4", "SSE_STD_HOIST=1"),
                                      ("SSE_FD_SINGLE_BUF=1", "SSE_FD_KQ=3")])
 def test_tuning_knob_variants_in_emulation(defines):
     """The -D tuning knobs tools/gpu_variants.sh sweeps on the GPU (elements per CTA of the
