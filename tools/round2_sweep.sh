@@ -4,6 +4,7 @@
 #   2. A/B of the split loop B (runtime switch) and of the -D tuning variants on the headline
 #      configuration (M=20) and on config 3.
 # Before the call, on the CPU:   python tools/build_variants.py $(cat tools/round2_variants.txt)
+# and take build/variants/ out of .gpurunignore so that the libraries travel to the box.
 mkdir -p gpurun_out
 S=$(date +%s); el() { echo "[t+$(( $(date +%s) - S ))s] $*"; }
 timeout 600 python -m pytest tests/test_gpu_time_integration.py tests/test_gpu_variants.py -m gpu -q > gpurun_out/t_new.log 2>&1; el "new GPU tests rc=$?"; tail -4 gpurun_out/t_new.log
