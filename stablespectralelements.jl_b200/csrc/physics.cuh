@@ -20,7 +20,17 @@
 #define SSE_SHARED16(name) extern __shared__ __align__(16) double name[]
 #define SSE_RCP_APPROX(y, x) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x))
 #define SSE_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// Ampere-style asynchronous global -> shared copies (LDGSTS), 8 bytes each
+#define SSE_CP_ASYNC8(dst, src)                                                     \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(                    \
+                   (unsigned)__cvta_generic_to_shared(dst)),                        \
+               "l"(src) : "memory")
+#define SSE_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define SSE_CP_ASYNC_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
 #else
+#define SSE_CP_ASYNC8(dst, src) (*(dst) = *(src))
+#define SSE_CP_ASYNC_COMMIT() ((void)0)
+#define SSE_CP_ASYNC_WAIT(n) ((void)0)
 #define SSE_RCP_APPROX(y, x) y = emu_rcp_approx(x)
 #define SSE_PREFETCH_L2(p) ((void)(p))
 #endif

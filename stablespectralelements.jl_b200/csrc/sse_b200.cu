@@ -54,6 +54,9 @@ static int fail(const char* fmt, ...) {
 #ifndef SSE_STD_NB
 #define SSE_STD_NB 4      // k_standard_tensor (loop B)
 #endif
+#ifndef SSE_STD_PIPE_NB
+#define SSE_STD_PIPE_NB 2 // k_standard_tensor_pipe: 2 x 29 KB of stages + 17 KB -> 3 CTAs per SM
+#endif
 #ifndef SSE_NODAL_NB
 #define SSE_NODAL_NB 8    // k_nodal_batched (loop A)
 #endif
@@ -91,6 +94,7 @@ struct sse_handle {
   double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
   double* erk_u = nullptr;      //               stage state
   int erk_stages = 0;
+  int std_pipe = 0;             // 1: k_standard_tensor_pipe (SSE_B200_STD_PIPE=1)
   int split_b = 0;              // 1: loop B as k_fluxdiff_volume + k_fluxdiff_facet (SSE_B200_SPLIT_B=1)
   double* r_q = nullptr;        //    nodal residual handed from the volume to the facet kernel
   int split_copy_streams = 0;   // 1: sse_download_dudt_range copies on d2h_stream (sse_set_copy_streams)
@@ -317,6 +321,24 @@ static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
   CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, KC, NB>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
+  if (h->std_pipe) {   // opt-in: persistent CTAs, inputs staged one batch ahead with cp.async
+    const size_t smem_p = smem + sizeof(double) * 2 * (size_t)STStage<DIM, N1, NB>::size;
+    static int sms = 0, resident = 0;   // per instantiation
+    CU(cudaFuncSetAttribute(k_standard_tensor_pipe<DIM, N1, LAW, KC, NB>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    if (!sms) {
+      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &resident, k_standard_tensor_pipe<DIM, N1, LAW, KC, NB>, 128, smem_p));
+      if (resident < 1) return fail("k_standard_tensor_pipe does not fit on an SM");
+    }
+    const int pgrid = std::min(grid, sms * resident);
+    k_standard_tensor_pipe<DIM, N1, LAW, KC, NB> SSE_LAUNCH(pgrid, 128, smem_p, h->stream)(
+        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
   k_standard_tensor<DIM, N1, LAW, KC, NB> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
   h->launches++;
@@ -357,9 +379,12 @@ static int run_a(sse_handle* h, const double* u_dev) {
 }
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
   switch (h->fast_std) {   // standard form, advection on collapsed simplices
-    case 303: return launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_NB>(h, dudt_dev, rk);
-    case 304: return launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_NB>(h, dudt_dev, rk);
-    case 305: return launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_NB>(h, dudt_dev, rk);
+    case 303: return h->std_pipe ? launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
+                                 : launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_NB>(h, dudt_dev, rk);
+    case 304: return h->std_pipe ? launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
+                                 : launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_NB>(h, dudt_dev, rk);
+    case 305: return h->std_pipe ? launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
+                                 : launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_NB>(h, dudt_dev, rk);
     default: break;
   }
   switch (h->fast_b) {
@@ -959,6 +984,10 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
+    {
+      const char* e = getenv("SSE_B200_STD_PIPE");
+      h->std_pipe = (e && atoi(e) == 1) ? 1 : 0;
+    }
     {   // opt-in: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
       const char* e = getenv("SSE_B200_SPLIT_B");
       if (h->fast_b && e && atoi(e) == 1) {

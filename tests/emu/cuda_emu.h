@@ -288,6 +288,10 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
   return cudaSuccess;
 }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) {
+  *n = 3;
+  return cudaSuccess;
+}
 
 // names (mangled) of the kernels launched since the last call, one per line
 extern "C" __attribute__((used)) const char* emu_launch_log() {

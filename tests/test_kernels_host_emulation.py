@@ -422,3 +422,33 @@ def test_split_loop_b_in_emulation(emu_lib, name, monkeypatch):
     finally:
         emu_lib.emu_set_order(0)
         d.close()
+
+
+@pytest.mark.parametrize("name", ["adv3d_tet_p4_ragged", "adv3d_tet_p3_straight"])
+def test_pipelined_standard_kernel_in_emulation(emu_lib, name, monkeypatch):
+    """Opt-in SSE_B200_STD_PIPE=1: k_standard_tensor_pipe (persistent CTAs, the inputs of batch
+    n+1 staged in shared memory with cp.async while batch n is computed; in the emulator the
+    copies are immediate, so this checks the staging layout, the double buffering and the batch
+    loop, not the asynchrony).  Same arithmetic -> bitwise the default kernel, in every thread
+    order."""
+    build, _ = CASES[name]
+    solver, u0 = build()
+    u = cases.rough_state(solver, u0, seed=8)
+    outs = {}
+    for pipe, order in (("0", 0), ("1", 0), ("1", 1), ("1", 2)):
+        monkeypatch.setenv("SSE_B200_STD_PIPE", pipe)
+        emu_lib.emu_set_order(order)
+        d = dev.DeviceResidual(solver)
+        try:
+            emu_lib.emu_launch_log()
+            dudt = np.full_like(u, np.nan)
+            d.residual_host(u, dudt)
+            assert ("k_standard_tensor_pipe" in emu_lib.emu_launch_log().decode()) == (pipe == "1")
+            outs[(pipe, order)] = dudt
+        finally:
+            emu_lib.emu_set_order(0)
+            d.close()
+    ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+    assert _rel(outs[("1", 0)], ref) < 1e-12
+    for key in outs:
+        assert np.array_equal(outs[key], outs[("0", 0)]), key
