@@ -1545,32 +1545,97 @@ __device__ __forceinline__ void standard_stage_fill(double* __restrict__ stg, co
   SSE_CP_ASYNC_COMMIT();
 }
 
+// Bulk variant of the fill (SSE_B200_STD_PIPE=2): the six per-batch input blocks are contiguous in
+// global memory over the NB elements of a batch, so ONE thread hands each of them to the copy
+// engine as a `cp.async.bulk` (UBLKCP) that completes on the stage's mbarrier -- 6 instructions
+// per batch instead of ~29 LDGSTS per thread.  Needs 16-byte aligned sources (an element's blocks
+// are 8-byte aligned, a batch of an even number of them starting at an even element is 16-byte
+// aligned) and a full batch; otherwise the caller falls back to the 8-byte cp.async fill.
+template <int DIM, int N1, int NB>
+__device__ __forceinline__ bool standard_stage_bulk_ok(const Geo& G, const double* __restrict__ u_q,
+                                                       const long long k0) {
+  using SG = STStage<DIM, N1, NB>;
+  constexpr int NQ = SG::NQ, NF = SG::NF, DD = DIM * DIM;
+  if (NB % 2 != 0 || k0 + NB > G.N_e) return false;
+  const unsigned long long a =
+      (unsigned long long)(G.L_q + k0 * DD * NQ) | (unsigned long long)(u_q + k0 * NQ) |
+      (unsigned long long)(G.J_q + k0 * NQ) | (unsigned long long)(G.J_f + k0 * NF) |
+      (unsigned long long)(G.nJf + k0 * NF * DIM) | (unsigned long long)(G.toff + k0 * NF);
+  return (a & 15ull) == 0;
+}
+
+template <int DIM, int N1, int NB>
+__device__ __forceinline__ void standard_stage_fill_bulk(double* __restrict__ stg, double* bar,
+                                                         const Geo& G,
+                                                         const double* __restrict__ u_q,
+                                                         const long long k0) {
+  using SG = STStage<DIM, N1, NB>;
+  constexpr int NQ = SG::NQ, NF = SG::NF, DD = DIM * DIM;
+  if (threadIdx.x == 0) {
+    SSE_MBAR_EXPECT_TX(bar, sizeof(double) * SG::size);
+    SSE_BULK_G2S(stg + SG::oL, G.L_q + k0 * DD * NQ, sizeof(double) * NB * DD * NQ, bar);
+    SSE_BULK_G2S(stg + SG::oU, u_q + k0 * NQ, sizeof(double) * NB * NQ, bar);
+    SSE_BULK_G2S(stg + SG::oJq, G.J_q + k0 * NQ, sizeof(double) * NB * NQ, bar);
+    SSE_BULK_G2S(stg + SG::oJf, G.J_f + k0 * NF, sizeof(double) * NB * NF, bar);
+    SSE_BULK_G2S(stg + SG::oN, G.nJf + k0 * NF * DIM, sizeof(double) * NB * NF * DIM, bar);
+    SSE_BULK_G2S(stg + SG::oT, G.toff + k0 * NF, sizeof(double) * NB * (NF / 2), bar);
+  }
+  SSE_CP_ASYNC_COMMIT();   // an empty group: keeps the wait_group count of the two fills uniform
+}
+
+// bulk = 0: cp.async fill (SSE_B200_STD_PIPE=1); bulk = 1: cp.async.bulk + mbarrier where the
+// batch allows it (SSE_B200_STD_PIPE=2).  The stages start at an even double (16-byte aligned).
 template <int DIM, int N1, int LAW, int KC, int NB>
 __global__ void __launch_bounds__(128)
 k_standard_tensor_pipe(FastTables F, Tables T, Geo G, Phys P, RK rk,
                        const double* __restrict__ u_q, const double* __restrict__ u_f,
-                       double* __restrict__ dudt) {
+                       double* __restrict__ dudt, const int bulk) {
   using SG = STStage<DIM, N1, NB>;
+  static_assert(NB % 2 != 0 || SG::size % 2 == 0, "both stages 16-byte aligned");
   SSE_SHARED16(sm);
-  double* stage0 = sm + STCfg<DIM, N1, LAW, KC, NB>::oX(T.N_p) + 2 * NB * SG::NQ;
+  double* stage0 = sm + ((STCfg<DIM, N1, LAW, KC, NB>::oX(T.N_p) + 2 * NB * SG::NQ + 1) & ~1);
+  double* bars = stage0 + 2 * SG::size;      // two mbarriers (8 bytes each), one per stage
   const long long nb = (G.N_e - G.k_begin + NB - 1) / NB;
   long long bt = blockIdx.x;
   if (bt >= nb) return;
-  standard_stage_fill<DIM, N1, LAW, KC, NB>(stage0, G, u_q, G.k_begin + bt * NB);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      SSE_MBAR_INIT(bars, 1);
+      SSE_MBAR_INIT(bars + 1, 1);
+      SSE_MBAR_INIT_FENCE();
+    }
+    __syncthreads();
+  }
+  unsigned parity = 0;                       // bit s: phase the next wait on stage s looks for
+  auto fill = [&](const int s, const long long k0) -> bool {
+    if (bulk && standard_stage_bulk_ok<DIM, N1, NB>(G, u_q, k0)) {
+      standard_stage_fill_bulk<DIM, N1, NB>(stage0 + s * SG::size, bars + s, G, u_q, k0);
+      return true;
+    }
+    standard_stage_fill<DIM, N1, LAW, KC, NB>(stage0 + s * SG::size, G, u_q, k0);
+    return false;
+  };
+  bool cur_bulk = fill(0, G.k_begin + bt * NB);
   for (int it = 0; bt < nb; bt += gridDim.x, ++it) {
-    double* cur = stage0 + (it & 1) * SG::size;
+    const int s = it & 1;
+    double* cur = stage0 + s * SG::size;
     const long long nxt = bt + gridDim.x;
+    bool nxt_bulk = false;
     if (nxt < nb) {
-      standard_stage_fill<DIM, N1, LAW, KC, NB>(stage0 + ((it + 1) & 1) * SG::size, G, u_q,
-                                                G.k_begin + nxt * NB);
+      nxt_bulk = fill(s ^ 1, G.k_begin + nxt * NB);
       SSE_CP_ASYNC_WAIT(1);      // everything but the group just committed has landed
     } else {
       SSE_CP_ASYNC_WAIT(0);
+    }
+    if (cur_bulk) {
+      SSE_MBAR_WAIT(bars + s, (parity >> s) & 1u);
+      parity ^= 1u << s;
     }
     __syncthreads();             // ... and is visible to the whole CTA
     standard_tensor_body<DIM, N1, LAW, KC, NB, true>(F, T, G, P, rk, u_q, u_f, dudt,
                                                      G.k_begin + bt * NB, sm, cur);
     __syncthreads();             // the working set and `cur` are free again
+    cur_bulk = nxt_bulk;
   }
 }
 

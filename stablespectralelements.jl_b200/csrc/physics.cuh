@@ -27,7 +27,41 @@
                "l"(src) : "memory")
 #define SSE_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define SSE_CP_ASYNC_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
+// Bulk asynchronous copies (TMA engine, UBLKCP) completing on a shared-memory mbarrier: source,
+// destination and size are multiples of 16 bytes
+#define SSE_SMEM_U32(p) ((unsigned)__cvta_generic_to_shared(p))
+#define SSE_MBAR_INIT(bar, n)                                                            \
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), "r"(n) : "memory")
+#define SSE_MBAR_INIT_FENCE() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
+#define SSE_MBAR_EXPECT_TX(bar, bytes)                                                   \
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), \
+               "r"((unsigned)(bytes)) : "memory")
+#define SSE_BULK_G2S(dst, src, bytes, bar)                                               \
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
+               ::"r"(SSE_SMEM_U32(dst)), "l"(src), "r"((unsigned)(bytes)), "r"(SSE_SMEM_U32(bar)) : "memory")
+// Every thread polls the phase; a wait that outlives any plausible copy traps instead of hanging
+// the device (a wrong byte count would otherwise spin forever).
+__device__ __forceinline__ void sse_mbar_wait(const void* bar, unsigned parity) {
+  const unsigned a = SSE_SMEM_U32(bar);
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) __trap();
+  }
+}
+#define SSE_MBAR_WAIT(bar, parity) sse_mbar_wait(bar, parity)
 #else
+// host emulation: the copy is done on the spot by the issuing fiber, the barrier ops are no-ops
+#define SSE_MBAR_INIT(bar, n) ((void)(bar))
+#define SSE_MBAR_INIT_FENCE() ((void)0)
+#define SSE_MBAR_EXPECT_TX(bar, bytes) ((void)(bar))
+#define SSE_BULK_G2S(dst, src, bytes, bar) memcpy((void*)(dst), (const void*)(src), (size_t)(bytes))
+#define SSE_MBAR_WAIT(bar, parity) ((void)(bar))
 #define SSE_CP_ASYNC8(dst, src) (*(dst) = *(src))
 #define SSE_CP_ASYNC_COMMIT() ((void)0)
 #define SSE_CP_ASYNC_WAIT(n) ((void)0)

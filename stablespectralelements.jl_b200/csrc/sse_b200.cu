@@ -94,7 +94,7 @@ struct sse_handle {
   double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
   double* erk_u = nullptr;      //               stage state
   int erk_stages = 0;
-  int std_pipe = 0;             // 1: k_standard_tensor_pipe (SSE_B200_STD_PIPE=1)
+  int std_pipe = 0;             // 1 / 2: k_standard_tensor_pipe (SSE_B200_STD_PIPE=1 / =2, bulk fill)
   int split_b = 0;              // 1: loop B as k_fluxdiff_volume + k_fluxdiff_facet (SSE_B200_SPLIT_B=1)
   double* r_q = nullptr;        //    nodal residual handed from the volume to the facet kernel
   int split_copy_streams = 0;   // 1: sse_download_dudt_range copies on d2h_stream (sse_set_copy_streams)
@@ -322,7 +322,8 @@ static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
   if (h->std_pipe) {   // opt-in: persistent CTAs, inputs staged one batch ahead with cp.async
-    const size_t smem_p = smem + sizeof(double) * 2 * (size_t)STStage<DIM, N1, NB>::size;
+    // + one double to start the stages at a 16-byte boundary, + two mbarriers (bulk fill)
+    const size_t smem_p = smem + sizeof(double) * (2 * (size_t)STStage<DIM, N1, NB>::size + 3);
     static int sms = 0, resident = 0;   // per instantiation
     CU(cudaFuncSetAttribute(k_standard_tensor_pipe<DIM, N1, LAW, KC, NB>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
@@ -334,7 +335,7 @@ static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
     }
     const int pgrid = std::min(grid, sms * resident);
     k_standard_tensor_pipe<DIM, N1, LAW, KC, NB> SSE_LAUNCH(pgrid, 128, smem_p, h->stream)(
-        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
+        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->std_pipe == 2 ? 1 : 0);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -986,7 +987,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = 0;
     {
       const char* e = getenv("SSE_B200_STD_PIPE");
-      h->std_pipe = (e && atoi(e) == 1) ? 1 : 0;
+      const int v = e ? atoi(e) : 0;   // 1: cp.async fill, 2: cp.async.bulk + mbarrier fill
+      h->std_pipe = (v == 1 || v == 2) ? v : 0;
     }
     {   // opt-in: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
       const char* e = getenv("SSE_B200_SPLIT_B");

@@ -10,6 +10,7 @@ sorts last among the GPU tests on purpose.
   interleaved with both loops; exercised here with two shards on one GPU (device copies as the
   halo transport), which is what checks its stream / event dependencies on real hardware."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -43,6 +44,13 @@ def test_split_loop_b_matches_the_fused_kernel(p, monkeypatch):
     assert np.max(np.abs(outs["0"] - outs["1"])) <= 1e-13 * np.max(np.abs(outs["0"]))
 
 
+def _pipe_modes():
+    # "2" (cp.async.bulk + mbarrier fill) has not run on hardware yet and is therefore left out of
+    # the routine suite: tools/round2_sweep.sh sets SSE_B200_TEST_EXPERIMENTAL=1 for its first run
+    # (a wrong transaction count traps after a bounded spin instead of hanging the device).
+    return ("0", "1", "2") if os.environ.get("SSE_B200_TEST_EXPERIMENTAL") == "1" else ("0", "1")
+
+
 @pytest.mark.parametrize("p,M", [(4, 5), (2, 6)])
 def test_pipelined_standard_kernel_matches_the_default(p, M, monkeypatch):
     """SSE_B200_STD_PIPE=1: k_standard_tensor_pipe (persistent CTAs, cp.async staging one batch
@@ -52,7 +60,7 @@ def test_pipelined_standard_kernel_matches_the_default(p, M, monkeypatch):
     solver, u0 = cases.advection_tet_case(p=p, M=M, lazy=True)
     u = cases.rough_state(solver, u0, seed=8)
     outs = {}
-    for pipe in ("0", "1"):
+    for pipe in _pipe_modes():
         monkeypatch.setenv("SSE_B200_STD_PIPE", pipe)
         d = dev.DeviceResidual(solver)
         try:
@@ -62,8 +70,9 @@ def test_pipelined_standard_kernel_matches_the_default(p, M, monkeypatch):
             outs[pipe] = dudt
         finally:
             d.close()
-    assert np.all(np.isfinite(outs["1"]))
-    assert np.max(np.abs(outs["0"] - outs["1"])) <= 1e-13 * np.max(np.abs(outs["0"]))
+    for pipe in _pipe_modes()[1:]:
+        assert np.all(np.isfinite(outs[pipe])), pipe
+        assert np.max(np.abs(outs["0"] - outs[pipe])) <= 1e-13 * np.max(np.abs(outs["0"])), pipe
 
 
 def _long_mesh_case(n_layers):
