@@ -51,7 +51,7 @@ __device__ __forceinline__ void sse_mbar_wait(const void* bar, unsigned parity) 
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     if (ok) return;
-    if (spin > (1u << 22)) __trap();
+    if (spin > (1u << 20)) __trap();
   }
 }
 #define SSE_MBAR_WAIT(bar, parity) sse_mbar_wait(bar, parity)
