@@ -454,3 +454,37 @@ def test_pipelined_standard_kernel_in_emulation(emu_lib, name, monkeypatch):
     assert _rel(outs[("1", 0)], ref) < 1e-12
     for key in outs:
         assert np.array_equal(outs[key], outs[("0", 0)]), key
+
+
+@pytest.mark.parametrize("name", ["adv3d_tet_p4_ragged", "adv3d_tet_p3_straight"])
+def test_bulk_pipeline_on_misaligned_ranges_in_emulation(emu_lib, name, monkeypatch):
+    """SSE_B200_STD_PIPE=2 on element ranges cut at an odd element, as a shard's interior /
+    boundary split produces them: the first range ends in a ragged batch, the second starts at an
+    odd element, where an element's 8-byte aligned blocks (N_q odd at p = 4) do not qualify for
+    the 16-byte bulk copies and the kernel must take its cp.async fill instead.  Bitwise the
+    default kernel's full-mesh result."""
+    build, _ = CASES[name]
+    solver, u0 = build()
+    u = cases.rough_state(solver, u0, seed=11)
+    monkeypatch.setenv("SSE_B200_STD_PIPE", "0")
+    d = dev.DeviceResidual(solver)
+    try:
+        ref = np.full_like(u, np.nan)
+        d.residual_host(u, ref)
+    finally:
+        d.close()
+    monkeypatch.setenv("SSE_B200_STD_PIPE", "2")
+    d = dev.DeviceResidual(solver)
+    try:
+        n_el = d.N_e
+        cut = (n_el // 2) | 1
+        emu_lib.emu_launch_log()
+        d.upload_and_nodal_values(u)
+        d.time_derivative_range(0, cut)
+        d.time_derivative_range(cut, n_el)
+        assert emu_lib.emu_launch_log().decode().count("k_standard_tensor_pipe") == 2
+        out = np.full_like(u, np.nan)
+        d.download_dudt(out)
+    finally:
+        d.close()
+    assert np.array_equal(out, ref)
