@@ -13,7 +13,7 @@
  *   V, V^T  WarpedTensorProductMap3D/2D mul!    src/MatrixFreeOperators/warped_product_{2d,3d}.jl
  *           (dense fallback otherwise)
  *   physics src/ConservationLaws/euler_navierstokes.jl:100-195, ConservationLaws.jl:132-156
- * Parity of this file is pinned through tests/test_c_oracle.py against the NumPy oracle, which
+ * Parity of this file is pinned through tests/test_oracle_invariants.py (C vs NumPy oracle), which
  * in turn reproduces the reference's golden L2 errors (see oracle/sse_oracle.py header).
  *
  * Arrays use the reference's (Julia, column-major) layout, 0-based indices.
@@ -208,10 +208,23 @@ static void mass_solve(const oracle_problem *P, int64_t k, double *rhs, double *
 }
 
 int oracle_threads(void) { return omp_get_max_threads(); }
+/* bench.py's reference arm: use every host core even when the launcher exported OMP_NUM_THREADS=1
+ * (torch.distributed.run does); the reference's own Threads.@threads runs on `julia -t auto`. */
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* u, dudt: (N_p, N_c, N_e); u_q: (N_q, N_c, N_e); u_f: (N_f, N_e, N_c) ("switched order",
  * Solvers.jl:205) -- both scratch arrays are caller-allocated like PreAllocatedArraysFirstOrder. */
+int oracle_residual_fluxdiff_range(const oracle_problem *P, const double *u, double *dudt, double *u_q,
+                                   double *u_f, int64_t k0, int64_t k1);
 int oracle_residual_fluxdiff(const oracle_problem *P, const double *u, double *dudt, double *u_q, double *u_f) {
+  return oracle_residual_fluxdiff_range(P, u, dudt, u_q, u_f, 0, P->N_e);
+}
+
+/* The two element loops restricted to [k0, k1) (bounded sample of a large mesh for bench.py's
+ * reference arm).  Loop B reads the exterior traces u_f of neighbours that may lie outside the
+ * range: the caller runs the full-range call once beforehand so that they hold valid values. */
+int oracle_residual_fluxdiff_range(const oracle_problem *P, const double *u, double *dudt, double *u_q,
+                                   double *u_f, int64_t k0, int64_t k1) {
   const int d = P->d, Np = P->N_p, Nq = P->N_q, Nf = P->N_f, Nc = P->N_c;
   const int64_t Ne = P->N_e;
   const int npf = Nf / P->num_faces;
@@ -225,7 +238,7 @@ int oracle_residual_fluxdiff(const oracle_problem *P, const double *u, double *d
     double *halfnJq = malloc(sizeof(double) * d * P->num_faces * Nq);
     /* ---- loop A: nodal_values! */
 #pragma omp for schedule(static)
-    for (int64_t k = 0; k < Ne; ++k) {
+    for (int64_t k = k0; k < k1; ++k) {
       double *uq = u_q + (int64_t)Nq * Nc * k;
       for (int c = 0; c < Nc; ++c) apply_V(P, u + (int64_t)Np * (c + Nc * k), uq + Nq * c, Z, Wt);
       if (P->proj == 0) {
@@ -266,7 +279,7 @@ int oracle_residual_fluxdiff(const oracle_problem *P, const double *u, double *d
     /* implicit barrier: all traces written */
     /* ---- loop B: time_derivative! */
 #pragma omp for schedule(static)
-    for (int64_t k = 0; k < Ne; ++k) {
+    for (int64_t k = k0; k < k1; ++k) {
       double *uq = u_q + (int64_t)Nq * Nc * k;
       const double *Lq = P->L_q + (int64_t)Nq * d * d * k;
       /* numerical flux, scaled by B J_f */

@@ -32,11 +32,20 @@ def _lib():
     lib = C.CDLL(LIB)
     lib.oracle_threads.restype = C.c_int
     lib.oracle_residual_fluxdiff.argtypes = [C.POINTER(Problem), dp, dp, dp, dp]
+    lib.oracle_residual_fluxdiff_range.argtypes = [C.POINTER(Problem), dp, dp, dp, dp, C.c_int64,
+                                                   C.c_int64]
+    lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_set_threads.restype = None
     return lib
 
 
 def num_threads():
     return _lib().oracle_threads()
+
+
+def set_threads(n):
+    """Use n OpenMP threads from now on (overrides an inherited OMP_NUM_THREADS)."""
+    _lib().oracle_set_threads(int(n))
 
 
 def make_residual(prob, warped=None):
@@ -113,5 +122,14 @@ def make_residual(prob, warped=None):
         assert rc == 0
         return out
 
+    def fn_range(u, out, k0, k1):
+        """Loops A and B on the elements [k0, k1) only, into the caller's ``out`` (the traces of
+        neighbours outside the range must be valid from an earlier full call)."""
+        rc = lib.oracle_residual_fluxdiff_range(C.byref(P), u.ctypes.data_as(dp),
+                                                out.ctypes.data_as(dp), u_q.ctypes.data_as(dp),
+                                                u_f.ctypes.data_as(dp), int(k0), int(k1))
+        assert rc == 0
+
+    fn.range = fn_range
     fn._keep = (keep, P)
     return fn

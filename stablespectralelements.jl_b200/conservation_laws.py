@@ -63,16 +63,24 @@ class InviscidBurgersEquation:
         return len(self.a)
 
 
-@dataclass(frozen=True)
 class ViscousBurgersEquation:
-    b: float
-    a: Tuple[float, ...] = (1.0,)
+    """``ViscousBurgersEquation(a, b)`` / ``ViscousBurgersEquation(b)`` with a = (1.0,)
+    (burgers.jl:20-48)."""
     pde_type = SecondOrder
     N_c = 1
+
+    def __init__(self, a, b=None):
+        if b is None:
+            a, b = (1.0,), a
+        self.a = tuple(float(x) for x in a)
+        self.b = float(b)
 
     @property
     def d(self):
         return len(self.a)
+
+    def __repr__(self):
+        return f"ViscousBurgersEquation(a={self.a}, b={self.b})"
 
 
 @dataclass(frozen=True)

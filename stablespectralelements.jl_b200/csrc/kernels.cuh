@@ -844,7 +844,7 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
 
 // ------------------------------------------------------------------------- halo
 // send[s*NC + c] = u_f[off(idx[s]) + c*N_f]  (node-major: per-peer segments are contiguous)
-__global__ void k_halo_pack(const double* __restrict__ u_f, const int* __restrict__ off, int n,
+static __global__ void k_halo_pack(const double* __restrict__ u_f, const int* __restrict__ off, int n,
                             int NC, int Nf, double* __restrict__ send) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n)
@@ -852,7 +852,7 @@ __global__ void k_halo_pack(const double* __restrict__ u_f, const int* __restric
 }
 
 // halo slot h lives at pseudo-element N_e + h / N_f, node h % N_f
-__global__ void k_halo_unpack(double* __restrict__ u_f, const double* __restrict__ recv, int n,
+static __global__ void k_halo_unpack(double* __restrict__ u_f, const double* __restrict__ recv, int n,
                               int NC, int Nf, long long N_e) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h < n) {
@@ -864,7 +864,7 @@ __global__ void k_halo_unpack(double* __restrict__ u_f, const double* __restrict
 
 // the same for the BR1 auxiliary-variable traces q_f [k][m][c][j]: DIM * NC doubles per node,
 // ordered [m][c].  off[s] = k * NC * Nf + j is the u_f offset of the node (sse_halo_setup).
-__global__ void k_halo_pack_aux(const double* __restrict__ q_f, const int* __restrict__ off, int n,
+static __global__ void k_halo_pack_aux(const double* __restrict__ q_f, const int* __restrict__ off, int n,
                                 int NC, int D, int Nf, double* __restrict__ send) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n) {
@@ -875,7 +875,7 @@ __global__ void k_halo_pack_aux(const double* __restrict__ q_f, const int* __res
   }
 }
 
-__global__ void k_halo_unpack_aux(double* __restrict__ q_f, const double* __restrict__ recv, int n,
+static __global__ void k_halo_unpack_aux(double* __restrict__ q_f, const double* __restrict__ recv, int n,
                                   int NC, int D, int Nf, long long N_e) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h < n) {
@@ -894,7 +894,7 @@ struct LinComb {
   double c[SSE_ERK_MAX_TERMS];
   const double* x[SSE_ERK_MAX_TERMS];
 };
-__global__ void k_lincomb(double* out, const double* base, LinComb L, long long n) {
+static __global__ void k_lincomb(double* out, const double* base, LinComb L, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     double acc = base[i];
@@ -903,7 +903,7 @@ __global__ void k_lincomb(double* out, const double* base, LinComb L, long long 
   }
 }
 
-__global__ void k_axpy_rk(double* __restrict__ u, double* __restrict__ k, const double* r,
+static __global__ void k_axpy_rk(double* __restrict__ u, double* __restrict__ k, const double* r,
                           double a, double b, double dt, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

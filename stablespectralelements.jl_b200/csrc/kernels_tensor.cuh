@@ -556,9 +556,6 @@ k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restric
 #ifndef SSE_FD_SINGLE_BUF
 #define SSE_FD_SINGLE_BUF 0
 #endif
-#ifndef SSE_STD_HOIST
-#define SSE_STD_HOIST 0      // k_standard_tensor: facet / Jacobian loads hoisted into the prologue
-#endif
 
 template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
 struct FDCfg {
@@ -975,21 +972,6 @@ k_fluxdiff_facet(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __r
 // thread are in flight.
 // shared (doubles): sPhi[NB][NQ] | sG[DIM][NB][NQ] | sFf[NB][NF] | sD[DIM][N1][N1] |
 //                   sR[NB][NQ] | sM[NB][Np] | sX[2*NB*NQ]
-// shared-memory stage of k_standard_tensor_pipe: the per-batch inputs, in doubles
-template <int DIM, int N1, int NB>
-struct STStage {
-  static constexpr int NQ = ipow(N1, DIM);
-  static constexpr int NF = TensorNF<DIM, N1, true>::value;
-  static constexpr int oL = 0;                              // L_q  [NB][D*D][NQ]
-  static constexpr int oU = oL + NB * DIM * DIM * NQ;       // u_q  [NB][NQ]
-  static constexpr int oJq = oU + NB * NQ;                  // J_q  [NB][NQ]
-  static constexpr int oJf = oJq + NB * NQ;                 // J_f  [NB][NF]
-  static constexpr int oN = oJf + NB * NF;                  // nJf  [NB][NF][D]
-  static constexpr int oT = oN + NB * NF * DIM;             // toff [NB][NF] (int32, NF even)
-  static constexpr int size = oT + NB * (NF / 2);
-  static_assert(NF % 2 == 0, "exterior offsets are staged in 8-byte units");
-};
-
 template <int DIM, int N1, int LAW, int KC, int NB>
 struct STCfg {
   static constexpr int NQ = ipow(N1, DIM);
@@ -1006,277 +988,6 @@ struct STCfg {
   }
 };
 
-// STAGED = false: the operands come straight from global memory (k_standard_tensor);
-// STAGED = true: from the shared-memory stage `stg` that k_standard_tensor_pipe filled with
-// cp.async one batch ahead.
-template <int DIM, int N1, int LAW, int KC, int NB, bool STAGED>
-__device__ __forceinline__ void standard_tensor_body(
-    const FastTables& F, const Tables& T, const Geo& G, const Phys& P, const RK& rk,
-    const double* __restrict__ u_q, const double* __restrict__ u_f, double* __restrict__ dudt,
-    const long long k0, double* __restrict__ sm, const double* __restrict__ stg) {
-  using Cf = STCfg<DIM, N1, LAW, KC, NB>;
-  constexpr int NQ = Cf::NQ, NF = Cf::NF;
-  constexpr int DD = DIM * DIM;
-  const int Np = T.N_p;
-  double* sPhi = sm + Cf::oPhi;
-  double* sG = sm + Cf::oG;
-  double* sFf = sm + Cf::oFf;
-  double* sD = sm + Cf::oD;
-  double* sR = sm + Cf::oR;
-  double* sM = sm + Cf::oM();
-  double* sX = sm + Cf::oX(Np);
-  const int tid = threadIdx.x;
-  const bool active = tid < NQ;
-  const int i = active ? tid : 0;
-  using SG = STStage<DIM, N1, NB>;
-  auto kof = [&](int b) { return min(k0 + b, G.N_e - 1); };
-  auto ldUq = [&](int b, int ii) -> double {
-    if constexpr (STAGED) return stg[SG::oU + b * NQ + ii];
-    else return __ldcg(u_q + kof(b) * NQ + ii);
-  };
-  auto ldLq = [&](int b, int c, int ii) -> double {
-    if constexpr (STAGED) return stg[SG::oL + (b * DD + c) * NQ + ii];
-    else return __ldcg(G.L_q + (kof(b) * DD + c) * NQ + ii);
-  };
-  auto ldJq = [&](int b, int ii) -> double {
-    if constexpr (STAGED) return stg[SG::oJq + b * NQ + ii];
-    else return __ldcg(G.J_q + kof(b) * NQ + ii);
-  };
-  auto ldJf = [&](int b, int j) -> double {
-    if constexpr (STAGED) return stg[SG::oJf + b * NF + j];
-    else return __ldcg(G.J_f + kof(b) * NF + j);
-  };
-  auto ldnJ = [&](int b, int j, int m) -> double {
-    if constexpr (STAGED) return stg[SG::oN + (b * NF + j) * DIM + m];
-    else return __ldcg(G.nJf + (kof(b) * NF + j) * DIM + m);
-  };
-  auto ldToff = [&](int b, int j) -> int {
-    if constexpr (STAGED) return reinterpret_cast<const int*>(stg + SG::oT)[b * NF + j];
-    else return __ldcg(G.toff + kof(b) * NF + j);
-  };
-
-  // (An L2 prefetch of the next wave's inputs, as in k_fluxdiff_tensor, was measured on this
-  // kernel: 1.283 vs 1.228 ms at 196 608 elements, i.e. 4.5 % SLOWER -- the kernel already keeps
-  // 44 independent loads per thread in flight and the extra requests only compete with them.)
-  for (int idx = tid; idx < DIM * N1 * N1; idx += 128) sD[idx] = __ldg(F.D1 + idx);
-
-#if SSE_STD_HOIST
-  // Variant (-DSSE_STD_HOIST=1): the facet data of the first round of phase 1 and the Jacobians
-  // of phase 3 are requested here, together with the volume data, so that a batch pays one DRAM
-  // round trip (+ the dependent exterior-trace gather) instead of four in a row.
-  const bool hfac = tid < NB * NF;            // this thread owns a facet node in the first round
-  const int hj = hfac ? tid % NF : 0, hb = hfac ? tid / NF : 0;
-  const long long hk = min(k0 + hb, G.N_e - 1);
-  const double hJf = ldJf(hb, hj);
-  const int hext = ldToff(hb, hj);
-  double hnJ[DIM], hum[1], hup[1], jq[NB];
-#pragma unroll
-  for (int m = 0; m < DIM; ++m) hnJ[m] = ldnJ(hb, hj, m);
-  hum[0] = __ldcg(u_f + hk * NF + hj);
-#pragma unroll
-  for (int b = 0; b < NB; ++b) jq[b] = active ? ldJq(b, i) : 1.0;
-#endif
-
-  double ha[NB][DIM];
-  // ---- phase 0: φ(u) and the metric scalars h_m at the volume nodes
-  if (active) {
-    double uu[NB], Lq[NB][DD];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const long long k = min(k0 + b, G.N_e - 1);
-      uu[b] = ldUq(b, i);
-#pragma unroll
-      for (int c = 0; c < DD; ++c) Lq[b][c] = ldLq(b, c, i);
-    }
-#if SSE_STD_HOIST
-    hup[0] = __ldcg(u_f + hext);     // dependent on toff: issued behind the volume loads
-#endif
-    const double hw = 0.5 * __ldg(T.W + i);
-    double gref[DD];
-#pragma unroll
-    for (int c = 0; c < DD; ++c) gref[c] = __ldg(T.Gref + i * DD + c);   // [m][l]
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      double la[DIM];   // Σ_n Λ_q[l,n] a_n
-#pragma unroll
-      for (int l = 0; l < DIM; ++l) {
-        double v = 0.0;
-#pragma unroll
-        for (int n = 0; n < DIM; ++n) v = fma(Lq[b][l + DIM * n], P.a[n], v);
-        la[l] = v;
-      }
-      const double phi = (LAW == LAW_ADV) ? uu[b] : 0.5 * uu[b] * uu[b];
-      sPhi[b * NQ + i] = phi;
-#pragma unroll
-      for (int m = 0; m < DIM; ++m) {
-        double v = 0.0;
-#pragma unroll
-        for (int l = m; l < DIM; ++l) v = fma(gref[m * DIM + l], la[l], v);   // upper triangular
-        ha[b][m] = hw * v;
-        sG[(m * NB + b) * NQ + i] = ha[b][m] * phi;
-      }
-    }
-  }
-#if SSE_STD_HOIST
-  if (!active) hup[0] = __ldcg(u_f + hext);
-#endif
-  __syncthreads();
-  // separable collapsed-face rows of R (see apply_R_t): shared a3-contraction of φ, kept in sR
-  // (free until phase 2)
-  const int ng = T.R_ng;
-  if (ng > 0) {
-    SSE_LOOP(idx, NB * ng * N1) {
-      const int a2 = idx % N1, g = (idx / N1) % ng, b = idx / (N1 * ng);
-      const double* s0 = sPhi + b * NQ + __ldg(T.R_gstart + g) + a2 * N1;
-      double acc = 0.0;
-#pragma unroll
-      for (int a3 = 0; a3 < N1; ++a3) acc = fma(T.R_r3[a3], s0[a3], acc);
-      sR[idx] = acc;
-    }
-    __syncthreads();
-  }
-  // ---- phase 1: facet nodes: f_f = B J_f (f* − ½ (a·n) (R φ))
-  for (int idx = tid; idx < NB * NF; idx += 128) {
-    const int j = idx % NF, b = idx / NF;
-    const long long k = min(k0 + b, G.N_e - 1);
-    const long long gj = k * NF + j;
-    double nfv[DIM], sl[2], fs[1];
-#if SSE_STD_HOIST
-    const bool first_round = (idx == tid);
-    const double Jf = first_round ? hJf : ldJf(b, j);
-    const int ext = first_round ? hext : ldToff(b, j);
-#else
-    const double Jf = ldJf(b, j);
-    const int ext = ldToff(b, j);
-#endif
-    const double iJf = frcp(Jf);
-    double an = 0.0;
-#pragma unroll
-    for (int m = 0; m < DIM; ++m) {
-#if SSE_STD_HOIST
-      nfv[m] = (first_round ? hnJ[m] : ldnJ(b, j, m)) * iJf;
-#else
-      nfv[m] = ldnJ(b, j, m) * iJf;
-#endif
-      an = fma(P.a[m], nfv[m], an);
-    }
-#if SSE_STD_HOIST
-    if (first_round) interface_flux_vals<DIM, LAW>(P, 0, hum, hup, nfv, sl, fs);
-    else
-#endif
-    interface_flux<DIM, LAW>(P, 0, u_f, k * NF + j, ext, NF, nfv, sl, fs);
-    const int rb = __ldg(T.R_rp + j);
-    const int desc = __ldg(T.R_desc + j);
-    const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
-    const double* ph = sPhi + b * NQ + start;
-    double rphi = 0.0;
-    if (cnt == N1) {
-#pragma unroll
-      for (int q = 0; q < N1; ++q) rphi = fma(__ldg(T.R_v + rb + q), ph[q * stride], rphi);
-    } else if (ng > 0 && cnt == N1 * N1 && stride == 1) {
-      const double* t0 = sR + (b * ng + __ldg(T.R_grp + j)) * N1;
-#pragma unroll
-      for (int a2 = 0; a2 < N1; ++a2) rphi = fma(__ldg(T.R_E + j * N1 + a2), t0[a2], rphi);
-    } else if (cnt == N1 * N1 && stride == 1) {
-      double part[N1];
-#pragma unroll
-      for (int q2 = 0; q2 < N1; ++q2) {
-        part[q2] = 0.0;
-#pragma unroll
-        for (int q = 0; q < N1; ++q)
-          part[q2] = fma(__ldg(T.R_v + rb + q2 * N1 + q), ph[q2 * N1 + q], part[q2]);
-      }
-#pragma unroll
-      for (int q2 = 0; q2 < N1; ++q2) rphi += part[q2];
-    } else {
-      for (int q = 0; q < cnt; ++q) rphi = fma(__ldg(T.R_v + rb + q), ph[q * stride], rphi);
-    }
-    sFf[b * NF + j] = __ldg(T.B + j) * Jf * fma(-0.5 * an, rphi, fs[0]);
-  }
-  __syncthreads();
-  // ---- phase 2: volume terms along the tensor lines + lifting
-  if (active) {
-    double r[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) r[b] = 0.0;
-#pragma unroll
-    for (int m = 0; m < DIM; ++m) {
-      constexpr int s0 = ipow(N1, DIM - 1), s1 = ipow(N1, DIM >= 2 ? DIM - 2 : 0);
-      const int stride = (m == 0) ? s0 : (m == 1 ? s1 : 1);
-      const int am = (i / stride) % N1;
-      const int line0 = i - am * stride;
-      const double* Dm = sD + m * N1 * N1;
-#pragma unroll
-      for (int q = 0; q < N1; ++q) {
-        const int jt = line0 + q * stride;
-        const double dt = Dm[q * N1 + am];   // D_m[q, a]  (transpose apply)
-        const double dd = Dm[am * N1 + q];   // D_m[a, q]
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          r[b] = fma(dt, sG[(m * NB + b) * NQ + jt], r[b]);
-          r[b] = fma(-dd * ha[b][m], sPhi[b * NQ + jt], r[b]);
-        }
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
-      const double rv = __ldg(F.Rv + kk * NQ + i);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) r[b] = fma(-rv, sFf[b * NF + j], r[b]);
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) sR[b * NQ + i] = r[b];
-  }
-  __syncthreads();
-  // ---- phase 3: dudt = M^-1 V^T r  (the NB elements ride along as NB "components")
-  if (DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
-    // M^-1 V^T r = V^T (W/J) (V V^T r): fused V V^T pass, scaling, one V^T
-    if constexpr (DIM == 3) apply_VtV_t<N1, NB, 1>(vtab(T), sR, sX);
-#if SSE_STD_HOIST
-    if (active) {
-      const double w = __ldg(T.W + i);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) sR[b * NQ + i] *= fdiv(w, jq[b]);
-    }
-#else
-    SSE_LOOP(idx, NB * NQ) {
-      const int ii = idx % NQ, b = idx / NQ;
-      const long long k = min(k0 + b, G.N_e - 1);
-      sR[idx] *= fdiv(__ldg(T.W + ii), ldJq(b, ii));
-    }
-#endif
-    __syncthreads();
-    apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
-    store_result(T, G, rk, k0, NB, 1, sM, dudt);
-    return;
-  }
-  apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
-  if (T.mass_kind == MASS_DIAGONAL) {
-    SSE_LOOP(idx, NB * NQ) {
-      const int ii = idx % NQ, b = idx / NQ;
-      const long long k = min(k0 + b, G.N_e - 1);
-      sM[idx] = fdiv(sM[idx], __ldg(T.W + ii) * ldJq(b, ii));
-    }
-    __syncthreads();
-  } else {
-    apply_V_t<DIM, N1, NB, 1>(vtab(T), sM, sR, sX);
-    SSE_LOOP(idx, NB * NQ) {
-      const int ii = idx % NQ, b = idx / NQ;
-      const long long k = min(k0 + b, G.N_e - 1);
-      sR[idx] *= fdiv(__ldg(T.W + ii), ldJq(b, ii));
-    }
-    __syncthreads();
-    apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
-  }
-  store_result(T, G, rk, k0, NB, 1, sM, dudt);
-}
-
-
-// The default kernel keeps its own copy of the body below (STAGED = false of
-// standard_tensor_body is the same algorithm): routing it through the template changed its
-// register allocation (a 16-byte spill), and the measured default binary is left untouched until
-// the variants have been timed on a GPU; unify then.
 template <int DIM, int N1, int LAW, int KC, int NB>
 __global__ void __launch_bounds__(128)
 k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
@@ -1304,23 +1015,6 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   // 44 independent loads per thread in flight and the extra requests only compete with them.)
   for (int idx = tid; idx < DIM * N1 * N1; idx += 128) sD[idx] = __ldg(F.D1 + idx);
 
-#if SSE_STD_HOIST
-  // Variant (-DSSE_STD_HOIST=1): the facet data of the first round of phase 1 and the Jacobians
-  // of phase 3 are requested here, together with the volume data, so that a batch pays one DRAM
-  // round trip (+ the dependent exterior-trace gather) instead of four in a row.
-  const bool hfac = tid < NB * NF;            // this thread owns a facet node in the first round
-  const int hj = hfac ? tid % NF : 0, hb = hfac ? tid / NF : 0;
-  const long long hk = min(k0 + hb, G.N_e - 1);
-  const long long hgj = hk * NF + hj;
-  const double hJf = __ldcg(G.J_f + hgj);
-  const int hext = __ldcg(G.toff + hgj);
-  double hnJ[DIM], hum[1], hup[1], jq[NB];
-#pragma unroll
-  for (int m = 0; m < DIM; ++m) hnJ[m] = __ldcg(G.nJf + hgj * DIM + m);
-  hum[0] = __ldcg(u_f + hk * NF + hj);
-#pragma unroll
-  for (int b = 0; b < NB; ++b) jq[b] = active ? __ldcg(G.J_q + min(k0 + b, G.N_e - 1) * NQ + i) : 1.0;
-#endif
 
   double ha[NB][DIM];
   // ---- phase 0: φ(u) and the metric scalars h_m at the volume nodes
@@ -1333,9 +1027,6 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 #pragma unroll
       for (int c = 0; c < DD; ++c) Lq[b][c] = __ldcg(G.L_q + (k * DD + c) * NQ + i);
     }
-#if SSE_STD_HOIST
-    hup[0] = __ldcg(u_f + hext);     // dependent on toff: issued behind the volume loads
-#endif
     const double hw = 0.5 * __ldg(T.W + i);
     double gref[DD];
 #pragma unroll
@@ -1362,9 +1053,6 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
       }
     }
   }
-#if SSE_STD_HOIST
-  if (!active) hup[0] = __ldcg(u_f + hext);
-#endif
   __syncthreads();
   // separable collapsed-face rows of R (see apply_R_t): shared a3-contraction of φ, kept in sR
   // (free until phase 2)
@@ -1386,29 +1074,15 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     const long long k = min(k0 + b, G.N_e - 1);
     const long long gj = k * NF + j;
     double nfv[DIM], sl[2], fs[1];
-#if SSE_STD_HOIST
-    const bool first_round = (idx == tid);
-    const double Jf = first_round ? hJf : __ldcg(G.J_f + gj);
-    const int ext = first_round ? hext : __ldcg(G.toff + gj);
-#else
     const double Jf = __ldcg(G.J_f + gj);
     const int ext = __ldcg(G.toff + gj);
-#endif
     const double iJf = frcp(Jf);
     double an = 0.0;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) {
-#if SSE_STD_HOIST
-      nfv[m] = (first_round ? hnJ[m] : __ldcg(G.nJf + gj * DIM + m)) * iJf;
-#else
       nfv[m] = __ldcg(G.nJf + gj * DIM + m) * iJf;
-#endif
       an = fma(P.a[m], nfv[m], an);
     }
-#if SSE_STD_HOIST
-    if (first_round) interface_flux_vals<DIM, LAW>(P, 0, hum, hup, nfv, sl, fs);
-    else
-#endif
     interface_flux<DIM, LAW>(P, 0, u_f, k * NF + j, ext, NF, nfv, sl, fs);
     const int rb = __ldg(T.R_rp + j);
     const int desc = __ldg(T.R_desc + j);
@@ -1478,19 +1152,11 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   if (DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
     // M^-1 V^T r = V^T (W/J) (V V^T r): fused V V^T pass, scaling, one V^T
     if constexpr (DIM == 3) apply_VtV_t<N1, NB, 1>(vtab(T), sR, sX);
-#if SSE_STD_HOIST
-    if (active) {
-      const double w = __ldg(T.W + i);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) sR[b * NQ + i] *= fdiv(w, jq[b]);
-    }
-#else
     SSE_LOOP(idx, NB * NQ) {
       const int ii = idx % NQ, b = idx / NQ;
       const long long k = min(k0 + b, G.N_e - 1);
       sR[idx] *= fdiv(__ldg(T.W + ii), __ldcg(G.J_q + k * NQ + ii));
     }
-#endif
     __syncthreads();
     apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
     store_result(T, G, rk, k0, NB, 1, sM, dudt);
@@ -1515,128 +1181,6 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
     apply_Vt_t<DIM, N1, NB, 1>(vtab(T), sR, sM, sX);
   }
   store_result(T, G, rk, k0, NB, 1, sM, dudt);
-}
-
-// Persistent, software-pipelined variant (opt-in, SSE_B200_STD_PIPE=1): each CTA walks over
-// batches of NB elements and fills the stage of batch n+1 with cp.async while it computes batch
-// n, so that the metric terms (92 % of the kernel's bytes) are in flight during ALL of a CTA's
-// life instead of only its load prologue.  8-byte copies: an element's blocks are only 8-byte
-// aligned (N_q = 125 doubles).
-template <int DIM, int N1, int LAW, int KC, int NB>
-__device__ __forceinline__ void standard_stage_fill(double* __restrict__ stg, const Geo& G,
-                                                    const double* __restrict__ u_q,
-                                                    const long long k0) {
-  using SG = STStage<DIM, N1, NB>;
-  constexpr int NQ = SG::NQ, NF = SG::NF, DD = DIM * DIM;
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const long long k = min(k0 + b, G.N_e - 1);
-    const double* srcs[6] = {G.L_q + k * DD * NQ, u_q + k * NQ, G.J_q + k * NQ, G.J_f + k * NF,
-                             G.nJf + k * NF * DIM,
-                             reinterpret_cast<const double*>(G.toff + k * NF)};
-    const int offs[6] = {SG::oL + b * DD * NQ, SG::oU + b * NQ, SG::oJq + b * NQ,
-                         SG::oJf + b * NF, SG::oN + b * NF * DIM, SG::oT + b * (NF / 2)};
-    const int cnts[6] = {DD * NQ, NQ, NQ, NF, NF * DIM, NF / 2};
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-      for (int q = tid; q < cnts[r]; q += 128) SSE_CP_ASYNC8(stg + offs[r] + q, srcs[r] + q);
-  }
-  SSE_CP_ASYNC_COMMIT();
-}
-
-// Bulk variant of the fill (SSE_B200_STD_PIPE=2): the six per-batch input blocks are contiguous in
-// global memory over the NB elements of a batch, so ONE thread hands each of them to the copy
-// engine as a `cp.async.bulk` (UBLKCP) that completes on the stage's mbarrier -- 6 instructions
-// per batch instead of ~29 LDGSTS per thread.  Needs 16-byte aligned sources (an element's blocks
-// are 8-byte aligned, a batch of an even number of them starting at an even element is 16-byte
-// aligned) and a full batch; otherwise the caller falls back to the 8-byte cp.async fill.
-template <int DIM, int N1, int NB>
-__device__ __forceinline__ bool standard_stage_bulk_ok(const Geo& G, const double* __restrict__ u_q,
-                                                       const long long k0) {
-  using SG = STStage<DIM, N1, NB>;
-  constexpr int NQ = SG::NQ, NF = SG::NF, DD = DIM * DIM;
-  if (NB % 2 != 0 || k0 + NB > G.N_e) return false;
-  const unsigned long long a =
-      (unsigned long long)(G.L_q + k0 * DD * NQ) | (unsigned long long)(u_q + k0 * NQ) |
-      (unsigned long long)(G.J_q + k0 * NQ) | (unsigned long long)(G.J_f + k0 * NF) |
-      (unsigned long long)(G.nJf + k0 * NF * DIM) | (unsigned long long)(G.toff + k0 * NF);
-  return (a & 15ull) == 0;
-}
-
-template <int DIM, int N1, int NB>
-__device__ __forceinline__ void standard_stage_fill_bulk(double* __restrict__ stg, double* bar,
-                                                         const Geo& G,
-                                                         const double* __restrict__ u_q,
-                                                         const long long k0) {
-  using SG = STStage<DIM, N1, NB>;
-  constexpr int NQ = SG::NQ, NF = SG::NF, DD = DIM * DIM;
-  if (threadIdx.x == 0) {
-    SSE_MBAR_EXPECT_TX(bar, sizeof(double) * SG::size);
-    SSE_BULK_G2S(stg + SG::oL, G.L_q + k0 * DD * NQ, sizeof(double) * NB * DD * NQ, bar);
-    SSE_BULK_G2S(stg + SG::oU, u_q + k0 * NQ, sizeof(double) * NB * NQ, bar);
-    SSE_BULK_G2S(stg + SG::oJq, G.J_q + k0 * NQ, sizeof(double) * NB * NQ, bar);
-    SSE_BULK_G2S(stg + SG::oJf, G.J_f + k0 * NF, sizeof(double) * NB * NF, bar);
-    SSE_BULK_G2S(stg + SG::oN, G.nJf + k0 * NF * DIM, sizeof(double) * NB * NF * DIM, bar);
-    SSE_BULK_G2S(stg + SG::oT, G.toff + k0 * NF, sizeof(double) * NB * (NF / 2), bar);
-  }
-  SSE_CP_ASYNC_COMMIT();   // an empty group: keeps the wait_group count of the two fills uniform
-}
-
-// bulk = 0: cp.async fill (SSE_B200_STD_PIPE=1); bulk = 1: cp.async.bulk + mbarrier where the
-// batch allows it (SSE_B200_STD_PIPE=2).  The stages start at an even double (16-byte aligned).
-template <int DIM, int N1, int LAW, int KC, int NB>
-__global__ void __launch_bounds__(128)
-k_standard_tensor_pipe(FastTables F, Tables T, Geo G, Phys P, RK rk,
-                       const double* __restrict__ u_q, const double* __restrict__ u_f,
-                       double* __restrict__ dudt, const int bulk) {
-  using SG = STStage<DIM, N1, NB>;
-  static_assert(NB % 2 != 0 || SG::size % 2 == 0, "both stages 16-byte aligned");
-  SSE_SHARED16(sm);
-  double* stage0 = sm + ((STCfg<DIM, N1, LAW, KC, NB>::oX(T.N_p) + 2 * NB * SG::NQ + 1) & ~1);
-  double* bars = stage0 + 2 * SG::size;      // two mbarriers (8 bytes each), one per stage
-  const long long nb = (G.N_e - G.k_begin + NB - 1) / NB;
-  long long bt = blockIdx.x;
-  if (bt >= nb) return;
-  if (bulk) {
-    if (threadIdx.x == 0) {
-      SSE_MBAR_INIT(bars, 1);
-      SSE_MBAR_INIT(bars + 1, 1);
-      SSE_MBAR_INIT_FENCE();
-    }
-    __syncthreads();
-  }
-  unsigned parity = 0;                       // bit s: phase the next wait on stage s looks for
-  auto fill = [&](const int s, const long long k0) -> bool {
-    if (bulk && standard_stage_bulk_ok<DIM, N1, NB>(G, u_q, k0)) {
-      standard_stage_fill_bulk<DIM, N1, NB>(stage0 + s * SG::size, bars + s, G, u_q, k0);
-      return true;
-    }
-    standard_stage_fill<DIM, N1, LAW, KC, NB>(stage0 + s * SG::size, G, u_q, k0);
-    return false;
-  };
-  bool cur_bulk = fill(0, G.k_begin + bt * NB);
-  for (int it = 0; bt < nb; bt += gridDim.x, ++it) {
-    const int s = it & 1;
-    double* cur = stage0 + s * SG::size;
-    const long long nxt = bt + gridDim.x;
-    bool nxt_bulk = false;
-    if (nxt < nb) {
-      nxt_bulk = fill(s ^ 1, G.k_begin + nxt * NB);
-      SSE_CP_ASYNC_WAIT(1);      // everything but the group just committed has landed
-    } else {
-      SSE_CP_ASYNC_WAIT(0);
-    }
-    if (cur_bulk) {
-      SSE_MBAR_WAIT(bars + s, (parity >> s) & 1u);
-      parity ^= 1u << s;
-    }
-    __syncthreads();             // ... and is visible to the whole CTA
-    standard_tensor_body<DIM, N1, LAW, KC, NB, true>(F, T, G, P, rk, u_q, u_f, dudt,
-                                                     G.k_begin + bt * NB, sm, cur);
-    __syncthreads();             // the working set and `cur` are free again
-    cur_bulk = nxt_bulk;
-  }
 }
 
 }  // namespace sse

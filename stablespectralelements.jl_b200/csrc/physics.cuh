@@ -20,51 +20,7 @@
 #define SSE_SHARED16(name) extern __shared__ __align__(16) double name[]
 #define SSE_RCP_APPROX(y, x) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x))
 #define SSE_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
-// Ampere-style asynchronous global -> shared copies (LDGSTS), 8 bytes each
-#define SSE_CP_ASYNC8(dst, src)                                                     \
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(                    \
-                   (unsigned)__cvta_generic_to_shared(dst)),                        \
-               "l"(src) : "memory")
-#define SSE_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
-#define SSE_CP_ASYNC_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
-// Bulk asynchronous copies (TMA engine, UBLKCP) completing on a shared-memory mbarrier: source,
-// destination and size are multiples of 16 bytes
-#define SSE_SMEM_U32(p) ((unsigned)__cvta_generic_to_shared(p))
-#define SSE_MBAR_INIT(bar, n)                                                            \
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), "r"(n) : "memory")
-#define SSE_MBAR_INIT_FENCE() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
-#define SSE_MBAR_EXPECT_TX(bar, bytes)                                                   \
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), \
-               "r"((unsigned)(bytes)) : "memory")
-#define SSE_BULK_G2S(dst, src, bytes, bar)                                               \
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
-               ::"r"(SSE_SMEM_U32(dst)), "l"(src), "r"((unsigned)(bytes)), "r"(SSE_SMEM_U32(bar)) : "memory")
-// Every thread polls the phase; a wait that outlives any plausible copy traps instead of hanging
-// the device (a wrong byte count would otherwise spin forever).
-__device__ __forceinline__ void sse_mbar_wait(const void* bar, unsigned parity) {
-  const unsigned a = SSE_SMEM_U32(bar);
-  for (unsigned spin = 0;; ++spin) {
-    unsigned ok;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (ok) return;
-    if (spin > (1u << 20)) __trap();
-  }
-}
-#define SSE_MBAR_WAIT(bar, parity) sse_mbar_wait(bar, parity)
 #else
-// host emulation: the copy is done on the spot by the issuing fiber, the barrier ops are no-ops
-#define SSE_MBAR_INIT(bar, n) ((void)(bar))
-#define SSE_MBAR_INIT_FENCE() ((void)0)
-#define SSE_MBAR_EXPECT_TX(bar, bytes) ((void)(bar))
-#define SSE_BULK_G2S(dst, src, bytes, bar) memcpy((void*)(dst), (const void*)(src), (size_t)(bytes))
-#define SSE_MBAR_WAIT(bar, parity) ((void)(bar))
-#define SSE_CP_ASYNC8(dst, src) (*(dst) = *(src))
-#define SSE_CP_ASYNC_COMMIT() ((void)0)
-#define SSE_CP_ASYNC_WAIT(n) ((void)0)
 #define SSE_RCP_APPROX(y, x) y = emu_rcp_approx(x)
 #define SSE_PREFETCH_L2(p) ((void)(p))
 #endif
@@ -131,7 +87,7 @@ __constant__ double c_lm[8] = {-1.0 / 3.0, -4.0 / 45.0, -44.0 / 945.0,   // 1/(1
                                1.0e-4, 0.0};
 
 // rare branch (|x-y|/(x+y) >= 1e-2): kept out of line so the common path stays small
-__device__ __noinline__ double logmean_full(double x, double y) { return (y - x) / log(y / x); }
+static __device__ __noinline__ double logmean_full(double x, double y) { return (y - x) / log(y / x); }
 
 // Taylor-branch values; f2 is returned so that callers can test both means with one branch
 __device__ __forceinline__ double logmean_taylor(double x, double y, double& f2) {
@@ -166,7 +122,7 @@ __device__ __forceinline__ double inv_logmean(double x, double y) {
 
 // both means of the Ranocha flux when at least one of them left the Taylor branch (rare):
 // .x = logmean(x0, y0), .y = inv_logmean(x1, y1)
-__device__ __noinline__ double2 logmeans_slow(double x0, double y0, double x1, double y1) {
+static __device__ __noinline__ double2 logmeans_slow(double x0, double y0, double x1, double y1) {
   return make_double2(logmean(x0, y0), inv_logmean(x1, y1));
 }
 

@@ -4,32 +4,16 @@
 // device-resident buffers once (north-star part (d)), derives the operator bundles the
 // reference builds in Solvers/operators.jl (S, C = R^T B, transposes), and launches the
 // element kernels of kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
-#ifdef SSE_HOST_EMU
-#include "cuda_emu.h"   // tests/emu: host emulation of the execution model, test builds only
-#else
-#include <cuda_runtime.h>
-#endif
+#include <map>
+#include <mutex>
 
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/sse_b200.h"
-#include "kernels.cuh"
-#include "kernels_tensor.cuh"
+#include "handle.h"
 #include "functionals.cuh"
 #include "geometry.cuh"
 
-using namespace sse;
-
 static thread_local std::string g_err;
 
-static int fail(const char* fmt, ...) {
+int sse_fail(const char* fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -38,77 +22,6 @@ static int fail(const char* fmt, ...) {
   g_err = buf;
   return -1;
 }
-
-#define CU(call)                                                                      \
-  do {                                                                                \
-    cudaError_t e_ = (call);                                                          \
-    if (e_ != cudaSuccess)                                                            \
-      return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                \
-                  cudaGetErrorString(e_));                                            \
-  } while (0)
-
-#define SSE_MAX_CHUNKS 32
-
-// Tuning knobs of the scalar standard-form kernels (elements per CTA riding along as components);
-// the defaults are the measured optimum, tools/gpu_variants.sh sweeps -D overrides.
-#ifndef SSE_STD_NB
-#define SSE_STD_NB 4      // k_standard_tensor (loop B)
-#endif
-#ifndef SSE_STD_PIPE_NB
-#define SSE_STD_PIPE_NB 2 // k_standard_tensor_pipe: 2 x 29 KB of stages + 17 KB -> 3 CTAs per SM
-#endif
-#ifndef SSE_NODAL_NB
-#define SSE_NODAL_NB 8    // k_nodal_batched (loop A)
-#endif
-
-struct sse_handle {
-  sse_config cfg{};
-  Tables T{};
-  Geo G{};
-  Phys P{};
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  cudaStream_t copy_stream = nullptr;
-  cudaStream_t d2h_stream = nullptr;          // second copy stream: D2H of finished chunks while
-                                              // later chunks are still being uploaded
-  // host-buffer pipeline: chunk_need[c] = bit mask of the element chunks that hold a neighbour
-  // of chunk c (loop B of c may start once loop A of those chunks is enqueued)
-  int n_chunk = 1;
-  uint32_t chunk_need[SSE_MAX_CHUNKS] = {};
-  cudaEvent_t ev_chunk[SSE_MAX_CHUNKS] = {};
-  unsigned next_ev = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<void*> allocs;
-  int64_t bytes = 0;
-  int64_t launches = 0;
-  // state / scratch
-  double *u = nullptr, *dudt = nullptr, *rk_k = nullptr;
-  double *u_q = nullptr, *u_f = nullptr, *q_q = nullptr, *q_f = nullptr;
-  int64_t n_state = 0, halo_elems = 0;
-  // halo
-  int* send_off = nullptr;
-  double *send_buf = nullptr, *recv_buf = nullptr;
-  int64_t n_send = 0;
-  // launch configuration
-  int second_order = 0, proj = 0, law_t = 0;
-  double* erk_k = nullptr;      // sse_erk_step: stage derivatives [erk_stages][n_state]
-  double* erk_u = nullptr;      //               stage state
-  int erk_stages = 0;
-  int std_pipe = 0;             // 1 / 2: k_standard_tensor_pipe (SSE_B200_STD_PIPE=1 / =2, bulk fill)
-  int split_b = 0;              // 1: loop B as k_fluxdiff_volume + k_fluxdiff_facet (SSE_B200_SPLIT_B=1)
-  double* r_q = nullptr;        //    nodal residual handed from the volume to the facet kernel
-  int split_copy_streams = 0;   // 1: sse_download_dudt_range copies on d2h_stream (sse_set_copy_streams)
-  int b_stages = 3;   // second order: bit 0 = auxiliary_variable! (A2), bit 1 = time_derivative!
-  int E_a = 1, E_b = 1, thr_a = 128, thr_b = 128;
-  size_t smem_a = 0, smem_b = 0;
-  // compile-time specialised tensor-product path
-  FastTables F{};
-  int fast_a = 0, fast_b = 0, n1 = 0, kc = 0, collapsed = 0;
-  int const_conflict = 0;
-  bool r_ap = false;
-  int fast_std = 0;
-  std::vector<std::vector<double>> S_dense;
-};
 
 template <typename Tp>
 static int dev_upload(sse_handle* h, const Tp* src, size_t n, Tp** out) {
@@ -240,113 +153,6 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
     default: return fail("unsupported dim/law combination");                         \
   }
 
-template <int DIM, int N1, int LAW>
-static int launch_a_fast(sse_handle* h, const double* u_dev) {
-  constexpr int EL = NodalCfg<DIM, N1>::E;
-  if (TensorNF<DIM, N1, true>::value != h->cfg.N_f)
-    return fail("facet-node count does not match the specialised kernel");
-  if constexpr (DIM == 3 && LawTraits<DIM, LAW>::NC == 1) {
-    if (h->proj == 0) {   // scalar law, no entropy projection: 8 elements per CTA as components
-      constexpr int NB = SSE_NODAL_NB;
-      const size_t smem = NodalBatchCfg<DIM, N1, NB>::bytes(h->cfg.N_p, h->cfg.N_f);
-      CU(cudaFuncSetAttribute(k_nodal_batched<DIM, N1, LAW, true, NB>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
-      k_nodal_batched<DIM, N1, LAW, true, NB> SSE_LAUNCH(grid, 128, smem, h->stream)(h->T, h->G, u_dev,
-                                                                             h->u_q, h->u_f);
-      h->launches++;
-      CU(cudaGetLastError());
-      return 0;
-    }
-  }
-  const size_t smem = NodalCfg<DIM, N1>::bytes(h->cfg.N_c, h->cfg.N_p, h->cfg.N_f);
-  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
-  {
-    static int sms = 0;
-    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const char* e = getenv("SSE_B200_PREFETCH");
-    h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_NODAL_MINB * EL;
-  }
-  k_nodal_tensor<DIM, N1, LAW, true> SSE_LAUNCH(grid, 128, smem, h->stream)(
-      h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
-static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
-  using Cf = FDCfg<DIM, N1, LAW, COLLAPSED, KC>;
-  if (Cf::NF != h->cfg.N_f) return fail("facet-node count does not match the specialised kernel");
-  const size_t smem = Cf::bytes(h->cfg.N_p);
-  CU(cudaFuncSetAttribute(k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
-  {
-    static int sms = 0;
-    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const char* e = getenv("SSE_B200_PREFETCH");
-    h->G.pf_dist = (e && atoi(e) == 0) ? 0 : sms * SSE_FD_MINB * Cf::EL;
-  }
-  if (h->split_b) {
-    const size_t smem_v = Cf::bytes_volume();
-    CU(cudaFuncSetAttribute(k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-    CU(cudaFuncSetAttribute(k_fluxdiff_facet<DIM, N1, LAW, COLLAPSED, KC>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Geo Gv = h->G;
-    if (Gv.pf_dist) Gv.pf_dist = Gv.pf_dist / SSE_FD_MINB * SSE_FD_VOL_MINB;
-    k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem_v, h->stream)(
-        h->F, h->T, Gv, h->P, h->u_q, h->r_q);
-    k_fluxdiff_facet<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
-        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->r_q);
-    h->launches += 2;
-    CU(cudaGetLastError());
-    return 0;
-  }
-  k_fluxdiff_tensor<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
-      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int DIM, int N1, int LAW, int KC, int NB>
-static int launch_std_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
-  using Cf = STCfg<DIM, N1, LAW, KC, NB>;
-  if (Cf::NF != h->cfg.N_f) return fail("facet-node count does not match the specialised kernel");
-  const size_t smem = Cf::bytes(h->cfg.N_p);
-  CU(cudaFuncSetAttribute(k_standard_tensor<DIM, N1, LAW, KC, NB>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (int)((h->G.N_e - h->G.k_begin + NB - 1) / NB);
-  if (h->std_pipe) {   // opt-in: persistent CTAs, inputs staged one batch ahead with cp.async
-    // + one double to start the stages at a 16-byte boundary, + two mbarriers (bulk fill)
-    const size_t smem_p = smem + sizeof(double) * (2 * (size_t)STStage<DIM, N1, NB>::size + 3);
-    static int sms = 0, resident = 0;   // per instantiation
-    CU(cudaFuncSetAttribute(k_standard_tensor_pipe<DIM, N1, LAW, KC, NB>,
-                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    if (!sms) {
-      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &resident, k_standard_tensor_pipe<DIM, N1, LAW, KC, NB>, 128, smem_p));
-      if (resident < 1) return fail("k_standard_tensor_pipe does not fit on an SM");
-    }
-    const int pgrid = std::min(grid, sms * resident);
-    k_standard_tensor_pipe<DIM, N1, LAW, KC, NB> SSE_LAUNCH(pgrid, 128, smem_p, h->stream)(
-        h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev, h->std_pipe == 2 ? 1 : 0);
-    h->launches++;
-    CU(cudaGetLastError());
-    return 0;
-  }
-  k_standard_tensor<DIM, N1, LAW, KC, NB> SSE_LAUNCH(grid, 128, smem, h->stream)(
-      h->F, h->T, h->G, h->P, rk, h->u_q, h->u_f, dudt_dev);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
 // instantiated (dim, n1, law) combinations of the specialised kernels
 static int fast_a_key(int dim, int n1, int law) {
   if ((dim == 2 || dim == 3) && n1 >= 3 && n1 <= 5 && (law == LAW_EULER || law == LAW_ADV))
@@ -361,42 +167,14 @@ static int fast_b_key(int dim, int n1, int law, int collapsed, int kc) {
 }
 
 static int run_a(sse_handle* h, const double* u_dev) {
-  switch (h->fast_a) {
-    case 232: return launch_a_fast<2, 3, LAW_EULER>(h, u_dev);
-    case 242: return launch_a_fast<2, 4, LAW_EULER>(h, u_dev);
-    case 252: return launch_a_fast<2, 5, LAW_EULER>(h, u_dev);
-    case 332: return launch_a_fast<3, 3, LAW_EULER>(h, u_dev);
-    case 342: return launch_a_fast<3, 4, LAW_EULER>(h, u_dev);
-    case 352: return launch_a_fast<3, 5, LAW_EULER>(h, u_dev);
-    case 230: return launch_a_fast<2, 3, LAW_ADV>(h, u_dev);
-    case 240: return launch_a_fast<2, 4, LAW_ADV>(h, u_dev);
-    case 250: return launch_a_fast<2, 5, LAW_ADV>(h, u_dev);
-    case 330: return launch_a_fast<3, 3, LAW_ADV>(h, u_dev);
-    case 340: return launch_a_fast<3, 4, LAW_ADV>(h, u_dev);
-    case 350: return launch_a_fast<3, 5, LAW_ADV>(h, u_dev);
-    default: break;
-  }
+  if (h->fast_a) return h->cfg.dim == 3 ? sse_launch_nodal_fast_3d(h, u_dev)
+                                        : sse_launch_nodal_fast_2d(h, u_dev);
   SSE_DISPATCH(launch_a, h, u_dev);
 }
 static int run_b(sse_handle* h, double* dudt_dev, const RK& rk) {
-  switch (h->fast_std) {   // standard form, advection on collapsed simplices
-    case 303: return h->std_pipe ? launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
-                                 : launch_std_fast<3, 3, LAW_ADV, 6, SSE_STD_NB>(h, dudt_dev, rk);
-    case 304: return h->std_pipe ? launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
-                                 : launch_std_fast<3, 4, LAW_ADV, 7, SSE_STD_NB>(h, dudt_dev, rk);
-    case 305: return h->std_pipe ? launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_PIPE_NB>(h, dudt_dev, rk)
-                                 : launch_std_fast<3, 5, LAW_ADV, 8, SSE_STD_NB>(h, dudt_dev, rk);
-    default: break;
-  }
-  switch (h->fast_b) {
-    case 203: return launch_b_fast<2, 3, LAW_EULER, true, 3>(h, dudt_dev, rk);
-    case 204: return launch_b_fast<2, 4, LAW_EULER, true, 3>(h, dudt_dev, rk);
-    case 205: return launch_b_fast<2, 5, LAW_EULER, true, 3>(h, dudt_dev, rk);
-    case 303: return launch_b_fast<3, 3, LAW_EULER, true, 6>(h, dudt_dev, rk);
-    case 304: return launch_b_fast<3, 4, LAW_EULER, true, 7>(h, dudt_dev, rk);
-    case 305: return launch_b_fast<3, 5, LAW_EULER, true, 8>(h, dudt_dev, rk);
-    default: break;
-  }
+  if (h->fast_std) return sse_launch_standard_fast(h, dudt_dev, rk);
+  if (h->fast_b) return h->cfg.dim == 3 ? sse_launch_fluxdiff_fast_3d(h, dudt_dev, rk)
+                                        : sse_launch_fluxdiff_fast_2d(h, dudt_dev, rk);
   SSE_DISPATCH(launch_b, h, dudt_dev, rk);
 }
 
@@ -483,6 +261,11 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     return fail("missing operator/geometry arrays");
 
   CU(cudaSetDevice(cfg->device));
+  CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+  {
+    const char* e = getenv("SSE_B200_PREFETCH");
+    h->prefetch = (e && atoi(e) == 0) ? 0 : 1;
+  }
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
@@ -543,23 +326,24 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       }
     }
     if (n >= 3 && n <= 5) {
-      // constant-bank copy of A for the specialised kernels (one slot per n); two handles with
-      // different A tables for the same n cannot share it
-      static double seen[3][25], seenB[3][125];
-      static bool have[3] = {false, false, false};
-      bool same = true;
-      for (int q = 0; q < n * n; ++q) same = same && (!have[n - 3] || seen[n - 3][q] == ops->warp_A[q]);
-      for (int q = 0; q < n * n * n; ++q)
-        same = same && (!have[n - 3] || seenB[n - 3][q] == ops->warp_B[q]);
-      if (!same) h->const_conflict = 1;
-      else {
-        for (int q = 0; q < n * n; ++q) seen[n - 3][q] = ops->warp_A[q];
-        for (int q = 0; q < n * n * n; ++q) seenB[n - 3][q] = ops->warp_B[q];
-        have[n - 3] = true;
-        CU(cudaMemcpyToSymbol(c_wA, ops->warp_A, sizeof(double) * n * n,
-                              sizeof(double) * 25 * (n - 3)));
-        CU(cudaMemcpyToSymbol(c_wB, ops->warp_B, sizeof(double) * n * n * n,
-                              sizeof(double) * 125 * (n - 3)));
+      // constant-bank copies of A and B for the specialised kernels (one slot per n, per device);
+      // two handles with different tables for the same n on one device cannot share them
+      static std::mutex mtx;
+      static std::map<std::pair<int, int>, std::vector<double>> seen;   // (device, n) -> A | B
+      std::lock_guard<std::mutex> lock(mtx);
+      std::vector<double> cur(ops->warp_A, ops->warp_A + n * n);
+      cur.insert(cur.end(), ops->warp_B, ops->warp_B + n * n * n);
+      auto it = seen.find({cfg->device, n});
+      if (it != seen.end() && it->second != cur) {
+        h->const_conflict = 1;
+      } else if (it == seen.end()) {
+        if (sse_tu_nodal2_set_constants(ops->warp_A, ops->warp_B, n) ||
+            sse_tu_nodal3_set_constants(ops->warp_A, ops->warp_B, n) ||
+            sse_tu_fluxdiff2_set_constants(ops->warp_A, ops->warp_B, n) ||
+            sse_tu_fluxdiff3_set_constants(ops->warp_A, ops->warp_B, n) ||
+            sse_tu_standard_set_constants(ops->warp_A, ops->warp_B, n))
+          return -1;
+        seen[{cfg->device, n}] = cur;
       }
     }
   } else if (cfg->v_kind == SSE_V_IDENTITY) {
@@ -985,12 +769,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
-    {
-      const char* e = getenv("SSE_B200_STD_PIPE");
-      const int v = e ? atoi(e) : 0;   // 1: cp.async fill, 2: cp.async.bulk + mbarrier fill
-      h->std_pipe = (v == 1 || v == 2) ? v : 0;
-    }
-    {   // opt-in: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
+    {   // measurement mode: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
       const char* e = getenv("SSE_B200_SPLIT_B");
       if (h->fast_b && e && atoi(e) == 1) {
         if (dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->r_q)) return -1;
@@ -1022,7 +801,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
   if (h->fast_b) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
-  if (h->fast_std) h->E_b = 4;                        // STCfg NB
+  if (h->fast_std) h->E_b = SSE_STD_NB;               // STCfg NB
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1668,3 +1447,16 @@ int64_t sse_kernel_launches(sse_handle* h) { return h ? h->launches : 0; }
 int64_t sse_device_bytes(sse_handle* h) { return h ? h->bytes : 0; }
 
 }  // extern "C"
+
+#ifdef SSE_HOST_EMU
+// host-emulation test build: one translation unit
+#define SSE_TU_DIM 2
+#include "tu_nodal.cu"
+#include "tu_fluxdiff.cu"
+#undef SSE_TU_DIM
+#define SSE_TU_DIM 3
+#include "tu_nodal.cu"
+#include "tu_fluxdiff.cu"
+#undef SSE_TU_DIM
+#include "tu_standard.cu"
+#endif

@@ -337,6 +337,15 @@ class DistributedResidual:
             self._exchange_and_time_derivative(dudt)     # loop B overlapped with the D2H copies
         self.dev.sync_copies()
 
+    def host_flow_name(self) -> str:
+        """Which host-buffer flow residual_host runs (reported by bench.py)."""
+        import os
+        if self.world == 1:
+            return "sse_residual(where=HOST): chunked H2D / loop A / loop B / D2H pipeline"
+        if os.environ.get("SSE_B200_SHARD_PIPELINE") == "1" and not self.second_order:
+            return "interleaved: boundary upload -> exchange || interior upload + loops A, B + D2H"
+        return "upload + loop A, exchange || interior loop B, boundary loop B, D2H by ranges"
+
     def timed_residuals(self, steps: int) -> float:
         """Milliseconds for ``steps`` residuals, CUDA events on the launching stream."""
         if self.world == 1:

@@ -14,7 +14,7 @@ CMD = ["g++", "-O1", "-std=c++17", "-DSSE_HOST_EMU", "-x", "c++", "-I", HERE, "-
 
 def _digest():
     h = hashlib.sha256(" ".join(CMD).encode())
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     files += [os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "sse_b200.h")]
     for f in files:
         with open(f, "rb") as fh:

@@ -74,6 +74,30 @@ CASES = {
     "golden_adv2d_tri": lambda: gc.advection_2d_tri(lazy=False)[:2],
     "golden_euler_vortex": lambda: gc.euler_vortex_2d_modal(lazy=False)[:2],
     "golden_adv3d_tet_dense_V": lambda: gc.advection_3d_tet(lazy=False)[:2],
+    # dispatch branches of VERDICT r1 rows a7 / a12 / a14 / a15 (also run on the emulator)
+    "adv2d_physical_skew": lambda: cases.advection_physical_case(d=2, p=3, M=3, lazy=False),
+    "adv2d_physical_standard": lambda: cases.advection_physical_case(d=2, p=3, M=3, lazy=False,
+                                                                     mapping="standard"),
+    "adv1d_physical": lambda: cases.advection_physical_case(d=1, p=4, M=5, lazy=False,
+                                                            mapping="standard"),
+    "burgers2d_physical": lambda: cases.burgers_physical_case(p=3, M=3, lazy=False),
+    "euler2d_standard_lf": lambda: cases.euler_standard_case(d=2, p=3, M=3, lazy=False),
+    "euler2d_standard_central_nodal": lambda: cases.euler_standard_case(
+        d=2, p=3, M=3, lazy=False, interface="central", approx="nodal"),
+    "euler3d_standard_lf": lambda: cases.euler_standard_case(d=3, p=2, M=2, lazy=False),
+    "euler3d_standard_lf_p4": lambda: cases.euler_standard_case(d=3, p=4, M=2, lazy=False),
+    "euler2d_standard_physical": lambda: cases.euler_standard_case(d=2, p=2, M=3, lazy=False,
+                                                                   strategy="physical"),
+    "euler2d_fluxdiff_conservative": lambda: cases.euler_conservative_fluxdiff_case(
+        p=3, M=3, lazy=False),
+    "mass_cholesky_standard": lambda: cases.mass_solver_case("cholesky", "standard", lazy=False),
+    "mass_cholesky_fluxdiff": lambda: cases.mass_solver_case("cholesky", "fluxdiff", lazy=False),
+    "mass_wa_full_standard": lambda: cases.mass_solver_case("wa_full", "standard", lazy=False),
+    "mass_wa_full_fluxdiff": lambda: cases.mass_solver_case("wa_full", "fluxdiff", lazy=False),
+    "mass_wa_diag_standard": lambda: cases.mass_solver_case("wa_diag", "standard", lazy=False),
+    "mass_wa_diag_fluxdiff": lambda: cases.mass_solver_case("wa_diag", "fluxdiff", lazy=False),
+    "viscous_burgers1d": lambda: cases.viscous_burgers_case(d=1, p=4, M=5, lazy=False),
+    "viscous_burgers2d": lambda: cases.viscous_burgers_case(d=2, p=3, M=3, lazy=False),
 }
 
 

@@ -1,11 +1,8 @@
-"""Opt-in variants that were written and checked on the host emulator after the round's GPU
-budget was spent: their first run on real hardware is this file, which
-sorts last among the GPU tests on purpose.
+"""Non-default paths of the library on real hardware (each also runs on the host emulator).
 
 * SSE_B200_SPLIT_B=1: loop B as k_fluxdiff_volume + k_fluxdiff_facet -- must reproduce the fused
   kernel to round-off (same per-node arithmetic, the nodal residual merely travels through
   global memory).
-* SSE_B200_STD_PIPE=1: the config-3 kernel as persistent CTAs with cp.async staging.
 * DistributedResidual._flow_host_interleaved: host-buffer residual of a shard with the upload
   interleaved with both loops; exercised here with two shards on one GPU (device copies as the
   halo transport), which is what checks its stream / event dependencies on real hardware."""
@@ -42,37 +39,6 @@ def test_split_loop_b_matches_the_fused_kernel(p, monkeypatch):
     # differently in the two instantiations, hence round-off rather than bitwise here (the
     # emulator build, which contracts nothing, is bitwise: test_kernels_host_emulation.py)
     assert np.max(np.abs(outs["0"] - outs["1"])) <= 1e-13 * np.max(np.abs(outs["0"]))
-
-
-def _pipe_modes():
-    # "2" (cp.async.bulk + mbarrier fill) has not run on hardware yet and is therefore left out of
-    # the routine suite: tools/round2_sweep.sh sets SSE_B200_TEST_EXPERIMENTAL=1 for its first run
-    # (a wrong transaction count traps after a bounded spin instead of hanging the device).
-    return ("0", "1", "2") if os.environ.get("SSE_B200_TEST_EXPERIMENTAL") == "1" else ("0", "1")
-
-
-@pytest.mark.parametrize("p,M", [(4, 5), (2, 6)])
-def test_pipelined_standard_kernel_matches_the_default(p, M, monkeypatch):
-    """SSE_B200_STD_PIPE=1: k_standard_tensor_pipe (persistent CTAs, cp.async staging one batch
-    ahead) against the default config-3 kernel; 6 M^3 elements, so that every CTA runs several
-    batches and both stages are reused."""
-    from sse_b200 import device as dev
-    solver, u0 = cases.advection_tet_case(p=p, M=M, lazy=True)
-    u = cases.rough_state(solver, u0, seed=8)
-    outs = {}
-    for pipe in _pipe_modes():
-        monkeypatch.setenv("SSE_B200_STD_PIPE", pipe)
-        d = dev.DeviceResidual(solver)
-        try:
-            dudt = np.full_like(u, np.nan)
-            for _ in range(2):
-                d.residual_host(u, dudt)
-            outs[pipe] = dudt
-        finally:
-            d.close()
-    for pipe in _pipe_modes()[1:]:
-        assert np.all(np.isfinite(outs[pipe])), pipe
-        assert np.max(np.abs(outs["0"] - outs[pipe])) <= 1e-13 * np.max(np.abs(outs["0"])), pipe
 
 
 def _long_mesh_case(n_layers):

@@ -75,6 +75,36 @@ CASES = {
     "advdiff2d_p3": (lambda: cases.advection_diffusion_case(d=2, p=3, M=3, lazy=True),
                      ["k_physicalILi2E"]),
     "golden_euler1d_gauss": (lambda: gc.euler_1d_gauss(lazy=True)[:2], ["k_fluxdiffILi1E"]),
+    # dispatch branches of VERDICT r1 rows a7 / a12 / a14 / a15
+    "adv2d_physical_skew": (lambda: cases.advection_physical_case(d=2, p=3, M=3),
+                            ["k_physicalILi2ELi0E"]),
+    "adv2d_physical_standard": (lambda: cases.advection_physical_case(d=2, p=3, M=3,
+                                                                      mapping="standard"),
+                                ["k_physicalILi2ELi0E"]),
+    "adv1d_physical": (lambda: cases.advection_physical_case(d=1, p=4, M=5, mapping="standard"),
+                       ["k_physicalILi1ELi0E"]),
+    "burgers2d_physical": (lambda: cases.burgers_physical_case(p=3, M=3), ["k_physicalILi2ELi1E"]),
+    "euler2d_standard_lf": (lambda: cases.euler_standard_case(d=2, p=3, M=3),
+                            ["k_standard_refILi2ELi2E"]),
+    "euler3d_standard_lf": (lambda: cases.euler_standard_case(d=3, p=2, M=2),
+                            ["k_standard_refILi3ELi2E"]),
+    "euler2d_standard_physical": (lambda: cases.euler_standard_case(d=2, p=2, M=3,
+                                                                    strategy="physical"),
+                                  ["k_physicalILi2ELi2E"]),
+    "euler2d_fluxdiff_conservative": (lambda: cases.euler_conservative_fluxdiff_case(p=3, M=3),
+                                      ["k_fluxdiff"]),
+    "mass_cholesky_standard": (lambda: cases.mass_solver_case("cholesky", "standard"),
+                               ["k_standard_refILi2E"]),
+    "mass_cholesky_fluxdiff": (lambda: cases.mass_solver_case("cholesky", "fluxdiff"),
+                               ["k_nodal_valuesILi2E", "k_fluxdiffILi2E"]),
+    "mass_wa_full_fluxdiff": (lambda: cases.mass_solver_case("wa_full", "fluxdiff"),
+                              ["k_nodal_valuesILi2E", "k_fluxdiffILi2E"]),
+    "mass_wa_diag_standard": (lambda: cases.mass_solver_case("wa_diag", "standard"),
+                              ["k_standard_refILi2E"]),
+    "mass_wa_diag_fluxdiff": (lambda: cases.mass_solver_case("wa_diag", "fluxdiff"),
+                              ["k_nodal_valuesILi2E", "k_fluxdiffILi2E"]),
+    "viscous_burgers1d": (lambda: cases.viscous_burgers_case(d=1, p=4, M=5), ["k_physicalILi1ELi1E"]),
+    "viscous_burgers2d": (lambda: cases.viscous_burgers_case(d=2, p=3, M=3), ["k_physicalILi2ELi1E"]),
 }
 
 
@@ -259,7 +289,7 @@ def test_general_explicit_rk_in_emulation(emu_lib):
         solver.close()
 
 
-@pytest.mark.parametrize("defines", [("SSE_STD_NB=2", "SSE_NODAL_NB=4", "SSE_STD_HOIST=1"),
+@pytest.mark.parametrize("defines", [("SSE_STD_NB=4", "SSE_NODAL_NB=4"),
                                      ("SSE_FD_SINGLE_BUF=1", "SSE_FD_KQ=3")])
 def test_tuning_knob_variants_in_emulation(defines):
     """The -D tuning knobs tools/gpu_variants.sh sweeps on the GPU (elements per CTA of the
@@ -422,69 +452,3 @@ def test_split_loop_b_in_emulation(emu_lib, name, monkeypatch):
     finally:
         emu_lib.emu_set_order(0)
         d.close()
-
-
-@pytest.mark.parametrize("name", ["adv3d_tet_p4_ragged", "adv3d_tet_p3_straight"])
-def test_pipelined_standard_kernel_in_emulation(emu_lib, name, monkeypatch):
-    """Opt-in SSE_B200_STD_PIPE=1: k_standard_tensor_pipe (persistent CTAs, the inputs of batch
-    n+1 staged in shared memory with cp.async while batch n is computed; in the emulator the
-    copies are immediate, so this checks the staging layout, the double buffering and the batch
-    loop, not the asynchrony).  Same arithmetic -> bitwise the default kernel, in every thread
-    order."""
-    build, _ = CASES[name]
-    solver, u0 = build()
-    u = cases.rough_state(solver, u0, seed=8)
-    outs = {}
-    # "2": the cp.async.bulk + mbarrier fill (one thread copies whole batches; ragged tail batches
-    # and misaligned ones fall back to the cp.async fill inside the same launch)
-    for pipe, order in (("0", 0), ("1", 0), ("1", 1), ("1", 2), ("2", 0), ("2", 1), ("2", 2)):
-        monkeypatch.setenv("SSE_B200_STD_PIPE", pipe)
-        emu_lib.emu_set_order(order)
-        d = dev.DeviceResidual(solver)
-        try:
-            emu_lib.emu_launch_log()
-            dudt = np.full_like(u, np.nan)
-            d.residual_host(u, dudt)
-            assert ("k_standard_tensor_pipe" in emu_lib.emu_launch_log().decode()) == (pipe != "0")
-            outs[(pipe, order)] = dudt
-        finally:
-            emu_lib.emu_set_order(0)
-            d.close()
-    ref = oc.semi_discrete_residual(oracle_problem(solver), u)
-    assert _rel(outs[("1", 0)], ref) < 1e-12
-    for key in outs:
-        assert np.array_equal(outs[key], outs[("0", 0)]), key
-
-
-@pytest.mark.parametrize("name", ["adv3d_tet_p4_ragged", "adv3d_tet_p3_straight"])
-def test_bulk_pipeline_on_misaligned_ranges_in_emulation(emu_lib, name, monkeypatch):
-    """SSE_B200_STD_PIPE=2 on element ranges cut at an odd element, as a shard's interior /
-    boundary split produces them: the first range ends in a ragged batch, the second starts at an
-    odd element, where an element's 8-byte aligned blocks (N_q odd at p = 4) do not qualify for
-    the 16-byte bulk copies and the kernel must take its cp.async fill instead.  Bitwise the
-    default kernel's full-mesh result."""
-    build, _ = CASES[name]
-    solver, u0 = build()
-    u = cases.rough_state(solver, u0, seed=11)
-    monkeypatch.setenv("SSE_B200_STD_PIPE", "0")
-    d = dev.DeviceResidual(solver)
-    try:
-        ref = np.full_like(u, np.nan)
-        d.residual_host(u, ref)
-    finally:
-        d.close()
-    monkeypatch.setenv("SSE_B200_STD_PIPE", "2")
-    d = dev.DeviceResidual(solver)
-    try:
-        n_el = d.N_e
-        cut = (n_el // 2) | 1
-        emu_lib.emu_launch_log()
-        d.upload_and_nodal_values(u)
-        d.time_derivative_range(0, cut)
-        d.time_derivative_range(cut, n_el)
-        assert emu_lib.emu_launch_log().decode().count("k_standard_tensor_pipe") == 2
-        out = np.full_like(u, np.nan)
-        d.download_dudt(out)
-    finally:
-        d.close()
-    assert np.array_equal(out, ref)

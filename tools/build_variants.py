@@ -19,15 +19,14 @@ OUT = os.path.join(ROOT, "build", "variants")
 def build(spec: str) -> str:
     name, defs = spec.split(":", 1)
     out = os.path.join(OUT, name + ".so")
-    cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared"] + ["-D" + d for d in defs.split(",") if d] + \
-          ["-o", out, os.path.join(CSRC, "sse_b200.cu")]
-    subprocess.run(cmd, check=True, cwd=CSRC)
-    return out
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    return ge.compile_library(out, defines=[d for d in defs.split(",") if d],
+                              objdir=os.path.join(ROOT, "build", "obj_" + name))
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2) // 2)) as pool:
+    with ThreadPoolExecutor(max_workers=2) as pool:
         for path in pool.map(build, sys.argv[1:]):
             print("built", path)
