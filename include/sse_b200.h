@@ -120,7 +120,9 @@ int sse_create(const sse_config* cfg, const sse_operators* ops, const sse_geomet
 int sse_destroy(sse_handle* h);
 
 /* semi_discrete_residual!(dudt, u, solver, t): u, dudt are (N_p, N_c, N_e).
- * where = SSE_HOST: pageable/pinned host pointers, copies included;
+ * where = SSE_HOST: pageable/pinned host pointers, copies included (u is uploaded into the
+ *   handle's device-resident state, i.e. it REPLACES whatever sse_set_state / the RK entry points
+ *   left there; the upload is ordered after work still queued on the handle's stream);
  * where = SSE_DEVICE: device pointers on cfg.device (no copies). */
 int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int where);
 
@@ -129,7 +131,9 @@ int sse_nodal_values(sse_handle* h, const double* u_dev);
 int sse_time_derivative(sse_handle* h, double* dudt_dev);
 
 /* Loop B on the local element range [k_begin, k_end) only (interior/boundary split that
- * overlaps the halo exchange). */
+ * overlaps the halo exchange).  First-order equations; for a second-order (BR1) equation a proper
+ * sub-range is an error here (time_derivative! would read stale q_f of the elements outside it):
+ * use sse_auxiliary_variable_range + sse_time_derivative_only_range below. */
 int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end);
 
 /* Device-resident state and fused low-storage (2N) Runge-Kutta:

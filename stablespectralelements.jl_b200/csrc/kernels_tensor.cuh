@@ -691,6 +691,7 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
   // ---- phase 0: stage nodal states and metric terms (kept in registers for the own node)
   if (active) {
     cons_to_state<DIM, LAW>(P, uu0, si);
+    if constexpr (LAW == LAW_EULER) euler_state_to_half<DIM>(si);
     if constexpr (PART != 2) {   // other nodes' states are only read by the volume term
 #pragma unroll
       for (int c = 0; c < NS2; ++c) sS2[c * nq + tid] = make_double2(si[2 * c], si[2 * c + 1]);
@@ -728,6 +729,7 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
       for (int m = 0; m < DIM; ++m) nfv[m] = nJ[m] * iJf;
       interface_flux<DIM, LAW>(P, P.two_point, u_f, k * NC * NF + j, ext, NF, nfv, sl, fs);
     }
+    if constexpr (LAW == LAW_EULER) euler_state_to_half<DIM>(sl);
     const double bj = __ldg(T.B + j) * Jf;
 #pragma unroll
     for (int c = 0; c < NC; ++c) sFf[(ee * NC + c) * NF + j] = bj * fs[c];
@@ -779,7 +781,8 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
               if constexpr (DIM == 3) cv[2] = fma(sv[m], Li[m + 2 * DIM] + sLb[m * nq + jt], cv[2]);
             }
           }
-          two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, cv, f);
+          if constexpr (LAW == LAW_EULER) ec_flux_half_c<DIM>(P, si, sj, cv, f);
+          else two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, cv, f);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             r[c] -= f[c];
@@ -850,18 +853,20 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
               double acc = 0.0;
 #pragma unroll
               for (int m = 0; m < DIM; ++m) acc = fma(Li[m + DIM * n], F.nref[fc * DIM + m], acc);
-              hq[n] = 0.5 * acc;
+              hq[n] = acc;                       // F.nref holds ½ n_ref
             }
           }
+          // the flux is linear in its direction vector: C[i,j] scales the direction (DIM
+          // products) instead of the NC flux components
 #pragma unroll
-          for (int n = 0; n < DIM; ++n) nJ[n] = hq[n] + sNf[n * nf + jj];
-          two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
+          for (int n = 0; n < DIM; ++n) nJ[n] = cij * (hq[n] + sNf[n * nf + jj]);
+          if constexpr (LAW == LAW_EULER) ec_flux_half_c<DIM>(P, si, sj, nJ, f);
+          else two_point_flux_c<DIM, LAW>(P, P.two_point, si, sj, nJ, f);
           double* dst = sX + (kk - half * KH) * NC * nq + tid;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            const double dlt = cij * f[c];
-            r[c] -= dlt;
-            dst[c * nq] = dlt;
+            r[c] -= f[c];
+            dst[c * nq] = f[c];
           }
           jp = jp_next;
           cij = cij_next;

@@ -556,7 +556,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
           h->F.slot_face[q] = f0;
         }
         if (slots_ok)
-          for (int q = 0; q < cfg->num_faces * d; ++q) h->F.nref[q] = ops->n_ref[q];
+          for (int q = 0; q < cfg->num_faces * d; ++q) h->F.nref[q] = 0.5 * ops->n_ref[q];   // ½ n_ref
         // work list of the facet-correction column sums (kernels_tensor.cuh, FastTables::red)
         {
           const int KHh = SSE_FD_KQ > 0 ? SSE_FD_KQ : (kc + 1) / 2;
@@ -765,7 +765,8 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
         (int)nd1 == Nq && mass_ok && h->r_ap && ops->Lambda_ref != nullptr &&
         Nf == (d == 3 ? 4 * n1 * n1 : 3 * n1))
       h->fast_a = fast_a_key(d, n1, law_t);
-    if (h->fast_b && !force_generic)
+    // (the specialised loop B hard-wires the entropy-conservative two-point flux)
+    if (h->fast_b && !force_generic && cfg->two_point_flux == SSE_TWO_POINT_ENTROPY_CONSERVATIVE)
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
@@ -860,6 +861,15 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
   const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
   const int nchunk = h->n_chunk;
   auto lo = [&](int c) { return (Ne * c) / nchunk; };
+  // every exit path leaves the handle's element range whole again
+  struct RangeGuard {
+    sse_handle* h;
+    ~RangeGuard() { h->G.k_begin = 0; h->G.N_e = h->cfg.N_e; }
+  } guard{h};
+  // the upload overwrites the resident state h->u: order it after whatever asynchronous work
+  // (sse_rk_stage, sse_erk_step, sse_nodal_values, ...) is still queued on the main stream
+  CU(cudaEventRecord(h->ev[3], h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev[3], 0));
   for (int c = 0; c < nchunk; ++c) {
     CU(cudaMemcpyAsync(h->u + lo(c) * blk, u + lo(c) * blk, (lo(c + 1) - lo(c)) * blk * sizeof(double),
                        cudaMemcpyHostToDevice, h->copy_stream));
@@ -1052,7 +1062,16 @@ int sse_erk_step(sse_handle* h, int n_stages, const double* A, const double* b, 
     for (int j = s; j < n_stages; ++j)
       if (A[s * n_stages + j] != 0.0) return fail("sse_erk_step: the tableau must be explicit");
   CU(cudaSetDevice(h->cfg.device));
-  if (h->erk_stages < n_stages) {      // (an earlier, smaller set stays owned by the handle)
+  if (h->erk_stages < n_stages) {
+    if (h->erk_k) {                    // release the smaller stage buffer of an earlier scheme
+      CU(cudaStreamSynchronize(h->stream));
+      h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)h->erk_k),
+                      h->allocs.end());
+      h->bytes -= (int64_t)h->erk_stages * h->n_state * (int64_t)sizeof(double);
+      cudaFree(h->erk_k);
+      h->erk_k = nullptr;
+      h->erk_stages = 0;
+    }
     if (dev_upload<double>(h, nullptr, (size_t)n_stages * h->n_state, &h->erk_k)) return -1;
     if (!h->erk_u && dev_upload<double>(h, nullptr, (size_t)h->n_state, &h->erk_u)) return -1;
     h->erk_stages = n_stages;
@@ -1156,6 +1175,12 @@ static int time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begi
 }
 
 int sse_time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begin, int64_t k_end) {
+  // Second order (BR1): time_derivative! reads the neighbours' auxiliary traces q_f, so running
+  // auxiliary_variable! on a sub-range only would consume stale q_f of the elements outside it.
+  if (h && h->second_order && !(k_begin == 0 && k_end == h->cfg.N_e))
+    return fail("sse_time_derivative_range: a second-order (BR1) equation needs the whole element "
+                "range here; for sub-ranges call sse_auxiliary_variable_range on all elements, "
+                "then sse_time_derivative_only_range");
   return time_derivative_range(h, dudt_dev, k_begin, k_end, 3);
 }
 
@@ -1244,7 +1269,11 @@ int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host
     if (!exact_q_host) return fail("the L2 error needs the exact solution at the volume nodes");
     const size_t n = (size_t)Nq * Nc * Ne;
     CU(cudaMalloc(&exact_dev, n * sizeof(double)));
-    CU(cudaMemcpyAsync(exact_dev, exact_q_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (cudaMemcpyAsync(exact_dev, exact_q_host, n * sizeof(double), cudaMemcpyHostToDevice,
+                        h->stream) != cudaSuccess) {
+      cudaFree(exact_dev);
+      return fail("functional: upload of the exact solution failed");
+    }
     xb = exact_dev;
   }
   const int nblk = (int)std::min<int64_t>(256, Ne);

@@ -452,3 +452,32 @@ def test_split_loop_b_in_emulation(emu_lib, name, monkeypatch):
     finally:
         emu_lib.emu_set_order(0)
         d.close()
+
+
+def test_second_order_subrange_is_refused(emu_lib):
+    """sse_time_derivative_range on a proper sub-range of a BR1 problem would run
+    auxiliary_variable! on that range only and then read stale neighbour q_f -- it must fail
+    loudly; the two-call sequence over sub-ranges reproduces the full call."""
+    solver, u0 = cases.advection_diffusion_case(d=2, p=3, M=3, lazy=True)
+    u = cases.rough_state(solver, u0, seed=5)
+    d = dev.DeviceResidual(solver)
+    try:
+        n = d.N_e
+        d.set_state(u)
+        d.nodal_values()
+        d.time_derivative()
+        full = np.empty_like(u)
+        d.download_dudt(full)
+        with pytest.raises(RuntimeError, match="second-order"):
+            d.time_derivative_range(0, n // 2)
+        d.time_derivative_range(0, n)                       # the whole range stays legal
+        d.nodal_values()
+        d.auxiliary_variable_range(0, n // 2)
+        d.auxiliary_variable_range(n // 2, n)
+        d.time_derivative_only_range(n // 3, n)
+        d.time_derivative_only_range(0, n // 3)
+        split = np.empty_like(u)
+        d.download_dudt(split)
+        assert np.array_equal(split, full)
+    finally:
+        d.close()
