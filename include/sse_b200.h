@@ -202,6 +202,9 @@ int sse_time_residual(sse_handle* h, int reps, int split, float* ms);
 /* FP64 FMA-chain microbenchmark (TFLOP/s, FMA = 2 flops): roofline denominator for the
  * FP64-bound flux-differencing kernel. */
 int sse_measure_fp64_peak(int device, double* tflops);
+/* The same for FP64 tensor-core instructions (mma.sync m8n8k4, dense 8x8x4 tiles): the measured
+ * basis of the decision NOT to use DMMA for the (p+1)-wide contractions. */
+int sse_measure_dmma_peak(int device, double* tflops);
 int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
 int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
 

@@ -22,18 +22,31 @@ struct FastTables {
   const double* Cv;    // [KC][NQ] C[i, j] = R[j, i] B[j]
   const double* Rv;    // [KC][NQ] R[j, i]
   const double* D1;    // [DIM][N1][N1] 1-D derivative matrices of D_eta (row-major)
-  // work list of the facet-correction column sums, one run per exchanged part: entry =
-  // facet node | comp << 16 (comp 15 = all components), -1 = idle lane; runs are padded so that
-  // the long (collapsed-face) sums fill whole warps.  red_off[p]..red_off[p+1] delimit part p.
-  const int* red;
-  int red_off[5];
-  // by value (constant bank, uniform indexing): face of ELL slot k (the same for every row) and
-  // the reference normals [face][DIM]
-  int slot_face[12];
+  // by value (constant bank, uniform indexing): the reference normals [face][DIM], times one half.
+  // The specialised kernels assume the CANONICAL facet layout of the collapsed tensor-product
+  // simplices (verified by sse_create, else the generic kernels run): volume node
+  // i = (a1, a2[, a3]) meets, in ELL slot k of its row of C = R^T B,
+  //   3-D: k=0: face 0 node (a1,a3) | k=1,2: face k node (a2,a3) | k=3+f: face 3 node (a1,f)
+  //   2-D: k=0: face 0 node a1      | k=1,2: face k node a2
+  // and a facet node of a line face collects the N1 nodes of one tensor line (direction 2 for
+  // face 0, direction 1 for faces 1 and 2), a node (a1,f) of the collapsed face the N1^2 nodes
+  // (a1,*,*) through slot 3+f.
   double nref[12];
 };
 
 __host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// facet node of ELL slot kk of volume node (a1, a2, a3) in the canonical layout (see FastTables)
+template <int DIM, int N1>
+__device__ __forceinline__ int canon_facet_node(int kk, int a1, int a2, int a3) {
+  constexpr int NPF = ipow(N1, DIM - 1);
+  if constexpr (DIM == 3) {
+    if (kk >= 3) return 3 * NPF + a1 * N1 + (kk - 3);
+    return kk * NPF + (kk == 0 ? a1 : a2) * N1 + a3;
+  } else {
+    return kk * NPF + (kk == 0 ? a1 : a2);
+  }
+}
 
 // the few table pointers the V / V^T applies need, passed BY VALUE to the out-of-line functions
 // (a reference to the kernel-parameter struct would force a local-memory copy of all of it).
@@ -623,6 +636,10 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
   const bool active = tid < nq;
   const int e = active ? tid / NQ : 0;
   const int i = active ? tid % NQ : 0;
+  // tensor coordinates of the own node, slowest first
+  const int ia1 = i / ipow(N1, DIM - 1);
+  const int ia2 = (i / ipow(N1, DIM >= 2 ? DIM - 2 : 0)) % N1;
+  const int ia3 = DIM == 3 ? i % N1 : 0;
 
   // L2 prefetch of the inputs of the CTA that will run in this slot one wave later (CTAs are
   // scheduled in blockIdx order, pf_dist = SMs x resident CTAs x EL elements ahead): its
@@ -821,8 +838,7 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
       __syncthreads();   // previous users of sX (pair buffers / previous part) are done
       if (active) {
         const int kend = (half + 1) * KH < KC ? (half + 1) * KH : KC;
-        // software-pipelined table reads: slot kk+1 is fetched while slot kk is evaluated
-        int jp = __ldg(F.Cj + (half * KH) * NQ + i);      // facet node (| face << 16, unused)
+        // software-pipelined table read: C[i, j] of slot kk+1 is fetched while slot kk is evaluated
         double cij = __ldg(F.Cv + (half * KH) * NQ + i);
         constexpr int FACET_UNROLL = SSE_FD_FACET_UNROLL;
         int fc_prev = -1;
@@ -832,10 +848,9 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
 #pragma unroll FACET_UNROLL
         for (int kk = half * KH; kk < kend; ++kk) {
           const int kn = (kk + 1 < kend) ? kk + 1 : kk;
-          const int jp_next = __ldg(F.Cj + kn * NQ + i);
           const double cij_next = __ldg(F.Cv + kn * NQ + i);
-          const int j = jp & 0xffff;
-          const int fc = F.slot_face[kk];     // uniform: slot k lies on the same face in every row
+          const int j = canon_facet_node<DIM, N1>(kk, ia1, ia2, ia3);
+          const int fc = kk < DIM ? kk : DIM;   // canonical layout: slots >= DIM lie on the last face
           const int jj = e * NF + j;
           double nJ[DIM], sj[2 * NS2], f[NC];
 #pragma unroll
@@ -868,54 +883,51 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
             r[c] -= f[c];
             dst[c * nq] = f[c];
           }
-          jp = jp_next;
           cij = cij_next;
         }
       }
       __syncthreads();
-      // f_f -= column sums of this part's terms: the terms of facet node j sit in ELL slot k at
-      // an arithmetic progression of volume nodes (R_desc).  The host-built work list gives
-      // every lane either one facet node with all components (N1-term sums) or one
-      // (node, component) pair of the collapsed face (N1^2-term sums), whole warps of each kind.
-      for (int t = F.red_off[half] + tid; t < F.red_off[half + 1]; t += 128) {
-        const int ent = __ldg(F.red + t);
-        if (ent < 0) continue;
-        const int j = ent & 0xffff, cm = ent >> 16;
-        const int desc = __ldg(T.R_desc + j);
-        const int kslot = (desc >> 27) & 31;
-        const int start = desc & 1023, stride = (desc >> 10) & 1023, cnt = (desc >> 20) & 127;
-#pragma unroll
-        for (int ee = 0; ee < EL; ++ee) {
-          const double* base = sX + (kslot - half * KH) * NC * nq + ee * NQ + start;
-          double* ff = sFf + ee * NC * NF + j;
-          if (cm == 15) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-              const double* bc = base + c * nq;
-              double acc = 0.0;
-              if (cnt == N1) {                       // one tensor line
-#pragma unroll
-                for (int q = 0; q < N1; ++q) acc += bc[q * stride];
-              } else {
-                for (int q = 0; q < cnt; ++q) acc += bc[q * stride];
-              }
-              ff[c * NF] -= acc;
-            }
+      // f_f -= column sums of this part's terms (canonical layout, see FastTables): per line
+      // slot one lane per (element, component, facet node) adds the N1 terms of its tensor line;
+      // per collapsed-face slot one lane per (element, component, a1) the N1^2 terms behind it.
+      {
+        constexpr int NPF = ipow(N1, DIM - 1);
+        const int k_lo = half * KH, k_hi = (half + 1) * KH < KC ? (half + 1) * KH : KC;
+        const int n_line = (k_hi < 3 ? k_hi : 3) - (k_lo < 3 ? k_lo : 3);   // line slots here
+        for (int it = tid; it < n_line * EL * NC * NPF; it += 128) {
+          const int g = it % NPF, c = (it / NPF) % NC, ee = (it / (NPF * NC)) % EL;
+          const int kk = k_lo + it / (NPF * NC * EL);
+          int start, stride;
+          if constexpr (DIM == 3) {
+            const int g1 = g / N1, g2 = g % N1;
+            start = kk == 0 ? g1 * N1 * N1 + g2 : g1 * N1 + g2;
+            stride = kk == 0 ? N1 : N1 * N1;
           } else {
-            const double* bc = base + cm * nq;
+            start = kk == 0 ? g * N1 : g;
+            stride = kk == 0 ? 1 : N1;
+          }
+          const double* bc = sX + ((kk - k_lo) * NC + c) * nq + ee * NQ + start;
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < N1; ++q) acc += bc[q * stride];
+          sFf[(ee * NC + c) * NF + kk * NPF + g] -= acc;
+        }
+        if constexpr (DIM == 3) {
+          const int c_lo = k_lo > 3 ? k_lo : 3;                 // collapsed-face slots of this part
+          const int n_col = k_hi > c_lo ? k_hi - c_lo : 0;
+          for (int it = tid; it < n_col * EL * NC * N1; it += 128) {
+            const int g1 = it % N1, c = (it / N1) % NC, ee = (it / (N1 * NC)) % EL;
+            const int kk = c_lo + it / (N1 * NC * EL);
+            const double* bc = sX + ((kk - k_lo) * NC + c) * nq + ee * NQ + g1 * N1 * N1;
+            double part[N1];
+#pragma unroll
+            for (int q2 = 0; q2 < N1; ++q2) part[q2] = bc[q2];
+#pragma unroll
+            for (int q = N1; q < N1 * N1; ++q) part[q % N1] += bc[q];
             double acc = 0.0;
-            if (cnt == N1 * N1 && stride == 1) {     // block behind a collapsed-face node
-              double part[N1];
 #pragma unroll
-              for (int q2 = 0; q2 < N1; ++q2) part[q2] = bc[q2];
-#pragma unroll
-              for (int q = N1; q < N1 * N1; ++q) part[q % N1] += bc[q];
-#pragma unroll
-              for (int q2 = 0; q2 < N1; ++q2) acc += part[q2];
-            } else {
-              for (int q = 0; q < cnt; ++q) acc += bc[q * stride];
-            }
-            ff[cm * NF] -= acc;
+            for (int q2 = 0; q2 < N1; ++q2) acc += part[q2];
+            sFf[(ee * NC + c) * NF + 3 * NPF + g1 * N1 + (kk - 3)] -= acc;
           }
         }
       }
@@ -926,7 +938,7 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
   if (active) {
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
-      const int j = __ldg(F.Cj + kk * NQ + i) & 0xffff;
+      const int j = canon_facet_node<DIM, N1>(kk, ia1, ia2, ia3);
       const double rv = __ldg(F.Rv + kk * NQ + i);
       const double* ff = sFf + e * NC * NF + j;
 #pragma unroll

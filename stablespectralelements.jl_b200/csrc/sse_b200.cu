@@ -548,39 +548,35 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
         if (dev_upload_vec(h, Cj, &h->F.Cj) || dev_upload_vec(h, Cvv, &h->F.Cv) ||
             dev_upload_vec(h, Rvv, &h->F.Rv) || dev_upload_vec(h, D1, &h->F.D1))
           return -1;
-        // face of every ELL slot (must not depend on the row) and the reference normals, by value
-        bool slots_ok = kc <= 12 && cfg->num_faces * d <= 12 && ops->n_ref != nullptr;
-        for (int q = 0; q < kc && slots_ok; ++q) {
-          const int f0 = Rt.ci[Rt.rp[0] + q] / T.npf;
-          for (int i = 0; i < Nq; ++i) slots_ok = slots_ok && (Rt.ci[Rt.rp[i] + q] / T.npf == f0);
-          h->F.slot_face[q] = f0;
+        // canonical facet layout of the collapsed tensor-product simplices (FastTables): ELL slot
+        // -> facet node by formula, and the rows of R as the tensor lines / collapsed-face blocks
+        // the specialised kernels sum over
+        bool slots_ok = collapsed && (d == 2 || d == 3) && cfg->num_faces == d + 1 &&
+                        cfg->num_faces * d <= 12 && ops->n_ref != nullptr &&
+                        kc == (d == 3 ? 3 + n1 : 3);
+        {
+          const int npf = d == 3 ? n1 * n1 : n1;
+          slots_ok = slots_ok && Nf == (d == 3 ? 4 : 3) * npf;
+          for (int i = 0; i < Nq && slots_ok; ++i) {
+            const int a1 = i / npf, a2 = (d == 3 ? (i / n1) % n1 : i % n1), a3 = d == 3 ? i % n1 : 0;
+            for (int q = 0; q < kc; ++q) {
+              int want;
+              if (d == 3) want = q >= 3 ? 3 * npf + a1 * n1 + (q - 3)
+                                        : q * npf + (q == 0 ? a1 : a2) * n1 + a3;
+              else want = q * npf + (q == 0 ? a1 : a2);
+              slots_ok = slots_ok && Rt.ci[Rt.rp[i] + q] == want;
+            }
+          }
+          // every row of R: the N1 nodes of its tensor line, or the N1^2 nodes behind a node of
+          // the collapsed face -- given the slot check above, the row lengths pin the rest
+          for (int j = 0; j < Nf && slots_ok; ++j) {
+            const int cnt = R.rp[j + 1] - R.rp[j];
+            const bool block_face = d == 3 && j >= 3 * npf;
+            slots_ok = slots_ok && cnt == (block_face ? n1 * n1 : n1);
+          }
         }
         if (slots_ok)
           for (int q = 0; q < cfg->num_faces * d; ++q) h->F.nref[q] = 0.5 * ops->n_ref[q];   // ½ n_ref
-        // work list of the facet-correction column sums (kernels_tensor.cuh, FastTables::red)
-        {
-          const int KHh = SSE_FD_KQ > 0 ? SSE_FD_KQ : (kc + 1) / 2;
-          const int nparts = (kc + KHh - 1) / KHh;
-          std::vector<int> red;
-          slots_ok = slots_ok && nparts <= 4;
-          for (int part = 0; part < nparts && slots_ok; ++part) {
-            h->F.red_off[part] = (int)red.size();
-            std::vector<int> lines, blocks;
-            for (int j = 0; j < Nf; ++j) {
-              const int b = R.rp[j], cnt = R.rp[j + 1] - b;
-              const int k = Rslot[b] - Rt.rp[R.ci[b]];
-              if (k / KHh != part) continue;
-              (cnt > n1 ? blocks : lines).push_back(j);
-            }
-            for (int j : blocks)
-              for (int c = 0; c < Nc; ++c) red.push_back(j | (c << 16));
-            while (red.size() % 32) red.push_back(-1);
-            for (int j : lines) red.push_back(j | (15 << 16));
-            while (red.size() % 32) red.push_back(-1);
-          }
-          for (int part = nparts; part <= 4; ++part) h->F.red_off[part] = (int)red.size();
-          if (dev_upload_vec(h, red, &h->F.red)) return -1;
-        }
         ok = ok && (slots_ok || cfg->form != SSE_FORM_FLUX_DIFFERENCING);
         h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
         h->fast_std = (cfg->form == SSE_FORM_STANDARD) ? 1 : 0;
@@ -1470,6 +1466,63 @@ int sse_measure_fp64_peak(int device, double* tflops) {
   cudaFree(out);
   *tflops = best;
   return 0;
+}
+
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput with the same protocol: the evidence for
+// the "tensor cores only if DMMA beats the FP64 CUDA-core path" clause of the north star.  Eight
+// independent accumulator tiles per warp; FMA = 2 flops, 8*8*4 FMAs per instruction.
+#ifndef SSE_HOST_EMU
+__global__ void k_dmma_peak(double* out, int iters, double seed) {
+  double a = seed + 1e-3 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  double c[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) c[t][0] = c[t][1] = seed + t;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+#endif
+
+int sse_measure_dmma_peak(int device, double* tflops) {
+  if (!tflops) return fail("null argument");
+#ifdef SSE_HOST_EMU
+  (void)device;
+  return fail("no tensor cores in the host emulation");
+#else
+  CU(cudaSetDevice(device));
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 2048;
+  double* out = nullptr;
+  CU(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU(cudaEventRecord(e0));
+    k_dmma_peak SSE_LAUNCH(blocks, threads)(out, iters, 1e-30);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    // per warp and iteration: 8 mma x (8*8*4) FMAs
+    double tf = 2.0 * 8.0 * 256.0 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+#endif
 }
 
 int64_t sse_kernel_launches(sse_handle* h) { return h ? h->launches : 0; }

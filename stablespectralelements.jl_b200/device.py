@@ -74,7 +74,8 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_geometry_build", "sse_geometry_free", "sse_copy_to_host",
            "sse_auxiliary_variable_range", "sse_time_derivative_only_range",
            "sse_halo_pack_aux", "sse_halo_unpack_aux", "sse_erk_step",
-           "sse_upload_range_and_nodal_values", "sse_set_copy_streams"]
+           "sse_upload_range_and_nodal_values", "sse_set_copy_streams",
+           "sse_measure_dmma_peak"]
 
 
 def load_library(path: Optional[str] = None, allow_emulation: bool = False):
@@ -120,6 +121,7 @@ def load_library(path: Optional[str] = None, allow_emulation: bool = False):
     lib.sse_device_bytes.argtypes = [vp]
     lib.sse_device_bytes.restype = C.c_int64
     lib.sse_measure_fp64_peak.argtypes = [C.c_int, c_d_p]
+    lib.sse_measure_dmma_peak.argtypes = [C.c_int, c_d_p]
     lib.sse_time_derivative_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
     lib.sse_set_stream.argtypes = [vp, vp]
     lib.sse_upload_state.argtypes = [vp, vp]
@@ -149,6 +151,15 @@ def measure_fp64_peak(device: int = 0) -> float:
     out = C.c_double()
     if lib.sse_measure_fp64_peak(device, C.byref(out)) != 0:
         raise RuntimeError("sse_measure_fp64_peak failed: " + lib.sse_last_error().decode())
+    return float(out.value)
+
+
+def measure_dmma_peak(device: int = 0) -> float:
+    """Measured FP64 tensor-core (mma.sync m8n8k4) throughput in TFLOP/s."""
+    lib = load_library()
+    out = C.c_double()
+    if lib.sse_measure_dmma_peak(device, C.byref(out)) != 0:
+        raise RuntimeError("sse_measure_dmma_peak failed: " + lib.sse_last_error().decode())
     return float(out.value)
 
 

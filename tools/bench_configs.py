@@ -8,7 +8,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-import cases  # noqa: E402
+from sse_b200 import problems as cases  # noqa: E402
 
 
 def run(name, builder, bytes_per_elt, reps=10):
