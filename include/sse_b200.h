@@ -257,6 +257,59 @@ enum sse_functional_kind {
 enum sse_functional_arg { SSE_ARG_STATE = 0, SSE_ARG_DUDT = 1 };
 int sse_functional(sse_handle* h, int which, int arg, const double* exact_q_host, double* out);
 
+/* ---- element-sharded multi-GPU residual (one process per GPU, NCCL over NVLink) -------------
+ * New relative to the reference (no distributed path there); what a multi-GPU
+ * semi_discrete_residual! needs, behind the same ABI so that a host rank makes ONE call per
+ * residual.  Rank r of W owns the contiguous element range [N_e r / W, N_e (r+1) / W) of the
+ * mesh's element ordering (sse_shard_range) and passes
+ *   cfg        with N_e = the GLOBAL element count (N_halo is ignored),
+ *   geo_local  the geometric factors of its OWN elements only,
+ *   mapP_cols  the columns [start, stop) of the global connectivity: (N_f, n_loc) GLOBAL 0-based
+ *              linear indices j' + N_f k' (the reference's mapP, SpatialDiscretizations/mesh.jl),
+ *   nccl_id128 the 128-byte ncclUniqueId obtained by ONE rank from sse_nccl_unique_id and
+ *              distributed by whatever the host launcher has (MPI_Bcast, a file, torch.distributed).
+ * NCCL is loaded at run time (libnccl.so.2); world = 1 needs neither NCCL nor an id.
+ * Per residual: loop A -> pack boundary traces -> grouped ncclSend/ncclRecv on a communication
+ * stream || loop B on the interior elements -> unpack -> loop B on the boundary elements
+ * (second-order equations exchange twice: u_f, then the BR1 auxiliary traces q_f).             */
+#define SSE_MAX_PEERS 64
+typedef struct sse_shard sse_shard;
+typedef struct {
+  int64_t start, stop;       /* global element range of the rank                              */
+  int64_t n_halo, n_send;    /* trace nodes received into halo slots / packed for sending      */
+  int64_t k_lo, k_hi;        /* local elements [k_lo, k_hi) read no halo value (the interior)  */
+  int32_t n_peers;
+  int32_t peers[SSE_MAX_PEERS];          /* ascending ranks this rank exchanges with           */
+  int64_t send_counts[SSE_MAX_PEERS];    /* trace nodes per peer, in packing order             */
+  int64_t recv_counts[SSE_MAX_PEERS];
+} sse_shard_plan;
+int sse_shard_range(int64_t N_e_global, int rank, int world, int64_t* start, int64_t* stop);
+/* Pure host arithmetic (no GPU, no communication): the partition of rank `rank`.  mapP_local
+ * (N_f * n_loc, out): local connectivity with halo slots numbered from N_f * n_loc, peer by peer
+ * and by the owner's global trace index; send_idx (capacity N_f * n_loc, out): the n_send local
+ * trace nodes to pack, in the order the receiving rank numbers its halo slots.                  */
+int sse_shard_plan_build(const int64_t* mapP_cols, int32_t N_f, int64_t N_e_global, int rank,
+                         int world, sse_shard_plan* plan, int64_t* mapP_local, int64_t* send_idx);
+int sse_nccl_unique_id(void* id128);
+int sse_shard_create(const sse_config* cfg, const sse_operators* ops, const sse_geometry* geo_local,
+                     const int64_t* mapP_cols, int rank, int world, const void* nccl_id128,
+                     sse_shard** out);
+int sse_shard_destroy(sse_shard* s);
+/* The rank's own handle: sse_set_state / sse_get_state / sse_functional / sse_state_ptr ... act
+ * on the shard (functionals return the rank's partial sums).                                   */
+sse_handle* sse_shard_handle(sse_shard* s);
+int sse_shard_get_plan(sse_shard* s, sse_shard_plan* plan);
+/* semi_discrete_residual! of the shard.  where = SSE_DEVICE: u / dudt are device pointers or
+ * NULL (the handle's resident state / dudt buffer), asynchronous; where = SSE_HOST: host buffers
+ * of the rank's (N_p, N_c, n_loc) slices, copies inside the call, synchronous.                  */
+int sse_shard_residual(sse_shard* s, const double* u, double* dudt, double t, int where);
+/* 2N Runge-Kutta on the sharded device-resident state (update fused into loop B's epilogue). */
+int sse_shard_rk_stage(sse_shard* s, double a, double b, double dt);
+int sse_shard_rk_step_ck54(sse_shard* s, double dt);
+/* `reps` device-resident residuals timed with CUDA events on the handle's stream (ms total). */
+int sse_shard_time_residual(sse_shard* s, int reps, float* ms);
+int sse_shard_sync(sse_shard* s);
+
 #ifdef __cplusplus
 }
 #endif

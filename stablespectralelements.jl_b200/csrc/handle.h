@@ -83,6 +83,9 @@ struct sse_handle {
   int erk_stages = 0;
   int sm_count = 0;             // SMs of cfg.device (grid / prefetch-distance sizing)
   int prefetch = 1;             // L2 prefetch one wave ahead in the specialised kernels
+  RK rk_override{};             // sse_shard_rk_stage: the RK epilogue of the range launches
+  int use_rk_override = 0;
+  int proj_split = 0;           // 1: loop B as k_fluxdiff_nodal + k_project_tet
   int split_b = 0;              // 1: loop B as k_fluxdiff_volume + k_fluxdiff_facet (measurement
                                 //    mode of the volume term on its own, SSE_B200_SPLIT_B=1)
   double* r_q = nullptr;        //    nodal residual handed from the volume to the facet kernel

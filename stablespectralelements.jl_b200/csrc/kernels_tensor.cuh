@@ -13,6 +13,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "vmap3.cuh"
+#include "vmap3b.cuh"
 
 namespace sse {
 
@@ -550,6 +551,98 @@ k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restric
   SSE_LOOP(idx, Ev * Nf) u_f[k0 * Nf + idx] = bufF[idx];
 }
 
+// ============================================================ projection on the batched engine
+// (A loop-A kernel on the same engine, E = 4 / 5 / 8 elements per CTA, was measured and deleted: it
+// executes 25 % fewer instructions than k_nodal_tensor but, at 10 KB of shared memory per element,
+// keeps 16-20 warps per SM instead of 40 and was 18-50 % slower: profiles/r2_engine_ab.md.)
+// k_project_tet: dudt = M^-1 V^T r for the nodal residual r [k][NC][NQ] that the loop-B kernel
+// leaves in global memory, with the weight-adjusted solver: V^T (W/J) (V V^T r), followed by the
+// dudt store or the fused low-storage Runge-Kutta update.  E elements per CTA on the batched
+// engine -- as the tail of the loop-B kernel (one element per CTA) the same algebra ran its ragged
+// stages at a quarter of the lanes and was 27 % of that kernel's time.
+// Columns: NC components of E = G * NCOL / NC consecutive elements, NCOL columns per work item of
+// the engine (systems: NCOL = NC, one element per item group; scalar laws: NCOL consecutive
+// ELEMENTS ride along as the columns of a group).
+template <int N1, int NC, int NCOL, int G>
+struct ProjectTetCfg {
+  using D = V3Dims<N1>;
+  static_assert((G * NCOL) % NC == 0, "whole elements per CTA");
+  static constexpr int NQ = D::N3, COLS = G * NCOL, E = COLS / NC;
+  static constexpr int oX = 0;
+  static constexpr int oZ = oX + COLS * NQ;
+  static constexpr int oM = oX;   // the modal result overlays X, dead once the last B^T has run
+  static constexpr size_t bytes = sizeof(double) * (size_t)(oZ + G * VBLayout<N1, NCOL>::ZG);
+  static constexpr int NR = (E * NQ + 127) / 128;
+};
+
+#ifndef SSE_PROJECT_TET_E
+#define SSE_PROJECT_TET_E 4
+#endif
+#ifndef SSE_PROJECT_TET_MINB
+#define SSE_PROJECT_TET_MINB 5
+#endif
+
+template <int N1, int NC, int NCOL, int G>
+__global__ void __launch_bounds__(128, SSE_PROJECT_TET_MINB)
+k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* __restrict__ dudt) {
+  using Cf = ProjectTetCfg<N1, NC, NCOL, G>;
+  using D = V3Dims<N1>;
+  constexpr int NQ = Cf::NQ, NR = Cf::NR, E = Cf::E;
+  const Geo& Gm = G_;
+  SSE_SHARED16(sm);
+  double* X = sm + Cf::oX;
+  double* Z = sm + Cf::oZ;
+  double* M = sm + Cf::oM;
+  const int tid = threadIdx.x;
+  const long long k0 = Gm.k_begin + (long long)blockIdx.x * E;
+  const V3Tab v3{T.wC, T.wCt, T.pairtab, T.modetab, T.wK};
+  for (int idx = tid; idx < E * NC * NQ; idx += 128) {   // asynchronous copies, all in flight
+    const int e = idx / (NC * NQ);
+    const long long k = min(k0 + e, Gm.N_e - 1);
+    SSE_CP_ASYNC8(X + idx, r_q + k * NC * NQ + (idx - e * NC * NQ));
+  }
+  double wij[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int idx = tid + r * 128;
+    wij[r] = 1.0;
+    if (idx < E * NQ) {
+      const int i = idx % NQ, e = idx / NQ;
+      wij[r] = fdiv(__ldg(T.W + i), __ldcg(Gm.J_q + min(k0 + e, Gm.N_e - 1) * NQ + i));
+    }
+  }
+  SSE_CP_ASYNC_WAIT_ALL();
+  __syncthreads();
+  vb_stageA<N1, NCOL, G, true>(tid, 128, X);
+  __syncthreads();
+  vb_stageB<N1, NCOL, G, true>(tid, 128, Z, X);
+  __syncthreads();
+  vb_stageK<N1, NCOL, G>(tid, 128, v3, Z);
+  __syncthreads();
+  vb_stageB<N1, NCOL, G, false>(tid, 128, Z, X);
+  __syncthreads();
+  vb_stageA<N1, NCOL, G, false>(tid, 128, X);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int idx = tid + r * 128;
+    if (idx < E * NQ) {
+      const int i = idx % NQ, e = idx / NQ;
+      double* xb = X + e * NC * NQ + i;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) xb[c * NQ] *= wij[r];
+    }
+  }
+  __syncthreads();
+  vb_stageA<N1, NCOL, G, true>(tid, 128, X);
+  __syncthreads();
+  vb_stageB<N1, NCOL, G, true>(tid, 128, Z, X);
+  __syncthreads();
+  vb_stageC<N1, NCOL, G, true>(tid, 128, v3, M, Z);
+  __syncthreads();
+  store_result(T, Gm, rk, k0, E, NC, M, dudt);
+}
+
 // ==================================================== loop B, flux-differencing form
 // Compile-time geometry of the specialised loop-B kernel: EL elements per 128-thread CTA,
 // NF facet nodes, and the shared-memory carve-up (in doubles; regions holding double2 start
@@ -607,7 +700,8 @@ struct FDCfg {
   }
 };
 
-// PART selects what the body does: 0 = the whole of loop B (the default, one fused kernel);
+// PART selects what the body does: 0 = the whole of loop B in one kernel; 3 = everything up to the
+// nodal residual r_q, which k_project_tet then projects (the default on tetrahedra);
 // 1 = volume flux differencing only, nodal residual written to r_q; 2 = everything else (interface
 // flux, facet correction, lift, projection, mass solve, epilogue), nodal residual read from r_q.
 // The split pair exists so that the volume kernel can run under its own register / shared-memory
@@ -944,9 +1038,17 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
 #pragma unroll
       for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
     }
+    if constexpr (PART == 3) {   // the projection runs as its own batched kernel (k_project_tet)
+      if (k0 + e < G.N_e) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
+        for (int c = 0; c < NC; ++c) r_q[((k0 + e) * NC + c) * NQ + i] = r[c];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) sR[(e * NC + c) * NQ + i] = r[c];
+    }
   }
+  if constexpr (PART == 3) return;
   __syncthreads();
   // ---- phase 6: dudt = M^-1 V^T r_q
   project_and_solve_t<DIM, N1, NC, EL>(T, G, k0, sR, sM, sX);
@@ -960,7 +1062,15 @@ k_fluxdiff_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
   fluxdiff_tensor_body<DIM, N1, LAW, COLLAPSED, KC, 0>(F, T, G, P, rk, u_q, u_f, dudt, nullptr);
 }
 
-// The split pair (opt-in): volume term under its own occupancy target, then the rest.
+// Loop B up to the nodal residual r_q (PART 3); k_project_tet finishes dudt = M^-1 V^T r_q.
+template <int DIM, int N1, int LAW, bool COLLAPSED, int KC>
+__global__ void __launch_bounds__(128, SSE_FD_MINB)
+k_fluxdiff_nodal(FastTables F, Tables T, Geo G, Phys P, const double* __restrict__ u_q,
+                 const double* __restrict__ u_f, double* __restrict__ r_q) {
+  fluxdiff_tensor_body<DIM, N1, LAW, COLLAPSED, KC, 3>(F, T, G, P, RK{}, u_q, u_f, nullptr, r_q);
+}
+
+// The split pair (measurement mode): volume term under its own occupancy target, then the rest.
 #ifndef SSE_FD_VOL_MINB
 #define SSE_FD_VOL_MINB 6
 #endif
@@ -1003,9 +1113,16 @@ struct STCfg {
   static __host__ __device__ constexpr size_t bytes(int Np) {
     return sizeof(double) * (size_t)(oX(Np) + 2 * NB * NQ);
   }
+  // without the projection tail: sR only serves as the scratch of the separable rows of R
+  static __host__ __device__ constexpr size_t bytes_nodal() {
+    return sizeof(double) * (size_t)(oM());
+  }
 };
 
-template <int DIM, int N1, int LAW, int KC, int NB>
+// PROJ = true: the projection / mass solve runs as the tail of this kernel; PROJ = false: the
+// nodal residual goes to global memory (dudt = r_q here) and k_project_tet finishes it, 25 elements
+// per CTA on the batched engine.
+template <int DIM, int N1, int LAW, int KC, int NB, bool PROJ>
 __global__ void __launch_bounds__(128)
 k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt) {
@@ -1161,9 +1278,16 @@ k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __
 #pragma unroll
       for (int b = 0; b < NB; ++b) r[b] = fma(-rv, sFf[b * NF + j], r[b]);
     }
+    if constexpr (!PROJ) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) sR[b * NQ + i] = r[b];
+      for (int b = 0; b < NB; ++b)
+        if (k0 + b < G.N_e) dudt[(k0 + b) * NQ + i] = r[b];
+    } else {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) sR[b * NQ + i] = r[b];
+    }
   }
+  if constexpr (!PROJ) return;
   __syncthreads();
   // ---- phase 3: dudt = M^-1 V^T r  (the NB elements ride along as NB "components")
   if (DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {

@@ -20,7 +20,16 @@
 #define SSE_SHARED16(name) extern __shared__ __align__(16) double name[]
 #define SSE_RCP_APPROX(y, x) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x))
 #define SSE_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// asynchronous global -> shared copies (LDGSTS), 8 bytes each: the batched kernels stage the
+// inputs of their E elements without a register round trip, every copy in flight at once
+#define SSE_CP_ASYNC8(dst, src)                                                     \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(                    \
+                   (unsigned)__cvta_generic_to_shared(dst)),                        \
+               "l"(src) : "memory")
+#define SSE_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_all;" ::: "memory")
 #else
+#define SSE_CP_ASYNC8(dst, src) (*(dst) = *(src))
+#define SSE_CP_ASYNC_WAIT_ALL() ((void)0)
 #define SSE_RCP_APPROX(y, x) y = emu_rcp_approx(x)
 #define SSE_PREFETCH_L2(p) ((void)(p))
 #endif

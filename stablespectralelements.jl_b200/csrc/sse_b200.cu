@@ -766,19 +766,35 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       h->fast_b = fast_b_key(d, h->n1, law_t, h->collapsed, h->kc);
     else
       h->fast_b = 0;
-    {   // measurement mode: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
-      const char* e = getenv("SSE_B200_SPLIT_B");
-      if (h->fast_b && e && atoi(e) == 1) {
-        if (dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->r_q)) return -1;
-        h->split_b = 1;
-      }
-    }
     if (h->fast_std && !force_generic && law_t == LAW_ADV && h->collapsed && h->n1 >= 3 &&
         h->n1 <= 5 && cfg->strategy == SSE_REFERENCE_OPERATOR &&
         d == 3 && h->kc == 3 + h->n1)
       h->fast_std = d * 100 + h->n1;
     else
       h->fast_std = 0;
+    {   // Collapsed tetrahedra, warped-product V, weight-adjusted M^-1 = I: the projection
+        // M^-1 V^T r of loop B runs as its own kernel on the batched engine (k_project_tet);
+        // SSE_B200_TET_ENGINE=0 keeps it as the tail of the loop-B kernel (the A/B reference)
+      const char* e = getenv("SSE_B200_TET_ENGINE");
+      const int want = e ? atoi(e) : 2;
+      const bool tet_ok = d == 3 && law_t == LAW_EULER && cfg->v_kind == SSE_V_WARPED &&
+                          cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED && !ops->Minv &&
+                          !h->const_conflict;
+      h->proj_split = (tet_ok && h->fast_b && (want & 2)) ? 1 : 0;
+      // the scalar standard-form kernel on tetrahedra (config 3) hands its nodal residual to the
+      // same projection kernel
+      const bool std_ok = d == 3 && cfg->v_kind == SSE_V_WARPED && !ops->Minv && !h->const_conflict &&
+                          cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED && h->fast_std > 0;
+      if (std_ok && (want & 2)) h->proj_split = 1;
+      if (h->proj_split && dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->r_q)) return -1;
+    }
+    {   // measurement mode: loop B as a volume kernel + a facet kernel (see fluxdiff_tensor_body)
+      const char* e = getenv("SSE_B200_SPLIT_B");
+      if (h->fast_b && e && atoi(e) == 1) {
+        if (!h->r_q && dev_upload<double>(h, nullptr, (size_t)Nq * Nc * Ne, &h->r_q)) return -1;
+        h->split_b = 1;
+      }
+    }
   }
   auto smem_a_fast = [&](int E) {
     // upper bound of NodalCfg::bytes (the launch computes the exact figure)
@@ -1159,7 +1175,7 @@ static int time_derivative_range(sse_handle* h, double* dudt_dev, int64_t k_begi
   if (k_begin < 0 || k_end > h->cfg.N_e || k_begin > k_end) return fail("bad element range");
   if (k_begin == k_end) return 0;
   CU(cudaSetDevice(h->cfg.device));
-  RK rk{};
+  RK rk = h->use_rk_override ? h->rk_override : RK{};
   h->G.k_begin = k_begin;
   h->G.N_e = k_end;
   h->b_stages = stages;
@@ -1532,6 +1548,7 @@ int64_t sse_device_bytes(sse_handle* h) { return h ? h->bytes : 0; }
 
 #ifdef SSE_HOST_EMU
 // host-emulation test build: one translation unit
+#include "tu_shard.cu"
 #define SSE_TU_DIM 2
 #include "tu_nodal.cu"
 #include "tu_fluxdiff.cu"

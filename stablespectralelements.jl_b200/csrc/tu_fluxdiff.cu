@@ -17,6 +17,24 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + Cf::EL - 1) / Cf::EL);
   h->G.pf_dist = h->prefetch ? h->sm_count * SSE_FD_MINB * Cf::EL : 0;
+  if constexpr (DIM == 3 && LAW == LAW_EULER) {
+    if (h->proj_split && !h->split_b) {   // loop B up to r_q, then the batched projection kernel
+      constexpr int EP = SSE_PROJECT_TET_E;
+      using Pf = ProjectTetCfg<N1, Cf::NC, Cf::NC, EP>;
+      CU(cudaFuncSetAttribute(k_fluxdiff_nodal<DIM, N1, LAW, COLLAPSED, KC>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(k_project_tet<N1, Cf::NC, Cf::NC, EP>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pf::bytes));
+      k_fluxdiff_nodal<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
+          h->F, h->T, h->G, h->P, h->u_q, h->u_f, h->r_q);
+      const int pgrid = (int)((h->G.N_e - h->G.k_begin + EP - 1) / EP);
+      k_project_tet<N1, Cf::NC, Cf::NC, EP> SSE_LAUNCH(pgrid, 128, Pf::bytes, h->stream)(
+          h->T, h->G, rk, h->r_q, dudt_dev);
+      h->launches += 2;
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
   if (h->split_b) {
     const size_t smem_v = Cf::bytes_volume();
     CU(cudaFuncSetAttribute(k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC>,

@@ -75,7 +75,22 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_auxiliary_variable_range", "sse_time_derivative_only_range",
            "sse_halo_pack_aux", "sse_halo_unpack_aux", "sse_erk_step",
            "sse_upload_range_and_nodal_values", "sse_set_copy_streams",
-           "sse_measure_dmma_peak"]
+           "sse_measure_dmma_peak", "sse_shard_range", "sse_shard_plan_build",
+           "sse_nccl_unique_id", "sse_shard_create", "sse_shard_destroy", "sse_shard_handle",
+           "sse_shard_get_plan", "sse_shard_residual", "sse_shard_rk_stage",
+           "sse_shard_rk_step_ck54", "sse_shard_time_residual", "sse_shard_sync"]
+
+
+SSE_MAX_PEERS = 64
+
+
+class SseShardPlan(C.Structure):
+    """sse_shard_plan of include/sse_b200.h."""
+    _fields_ = [("start", C.c_int64), ("stop", C.c_int64), ("n_halo", C.c_int64),
+                ("n_send", C.c_int64), ("k_lo", C.c_int64), ("k_hi", C.c_int64),
+                ("n_peers", C.c_int32), ("peers", C.c_int32 * SSE_MAX_PEERS),
+                ("send_counts", C.c_int64 * SSE_MAX_PEERS),
+                ("recv_counts", C.c_int64 * SSE_MAX_PEERS)]
 
 
 def load_library(path: Optional[str] = None, allow_emulation: bool = False):
@@ -140,6 +155,22 @@ def load_library(path: Optional[str] = None, allow_emulation: bool = False):
     lib.sse_erk_step.argtypes = [vp, C.c_int, c_d_p, c_d_p, C.c_double]
     lib.sse_upload_range_and_nodal_values.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int]
     lib.sse_set_copy_streams.argtypes = [vp, C.c_int]
+    lib.sse_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, c_i64_p, c_i64_p]
+    lib.sse_shard_plan_build.argtypes = [c_i64_p, C.c_int32, C.c_int64, C.c_int, C.c_int,
+                                         C.POINTER(SseShardPlan), c_i64_p, c_i64_p]
+    lib.sse_nccl_unique_id.argtypes = [vp]
+    lib.sse_shard_create.argtypes = [C.POINTER(SseConfig), C.POINTER(SseOperators),
+                                     C.POINTER(SseGeometry), c_i64_p, C.c_int, C.c_int, vp,
+                                     C.POINTER(vp)]
+    lib.sse_shard_destroy.argtypes = [vp]
+    lib.sse_shard_handle.argtypes = [vp]
+    lib.sse_shard_handle.restype = vp
+    lib.sse_shard_get_plan.argtypes = [vp, C.POINTER(SseShardPlan)]
+    lib.sse_shard_residual.argtypes = [vp, vp, vp, C.c_double, C.c_int]
+    lib.sse_shard_rk_stage.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.sse_shard_rk_step_ck54.argtypes = [vp, C.c_double]
+    lib.sse_shard_time_residual.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.sse_shard_sync.argtypes = [vp]
     if path is None:
         _LIB = lib
     return lib
@@ -152,6 +183,32 @@ def measure_fp64_peak(device: int = 0) -> float:
     if lib.sse_measure_fp64_peak(device, C.byref(out)) != 0:
         raise RuntimeError("sse_measure_fp64_peak failed: " + lib.sse_last_error().decode())
     return float(out.value)
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId for sse_shard_create (call on ONE rank, broadcast to the others)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.sse_nccl_unique_id(buf) != 0:
+        raise RuntimeError("sse_nccl_unique_id failed: " + lib.sse_last_error().decode())
+    return buf.raw
+
+
+def shard_plan(mapP_cols: np.ndarray, N_e_global: int, rank: int, world: int):
+    """sse_shard_plan_build (pure host): (plan, mapP_local (N_f, n_loc), send_idx) of ``rank`` from
+    the columns [start, stop) of the global connectivity ``mapP_cols`` (N_f, n_loc)."""
+    lib = load_library()
+    N_f, n_loc = mapP_cols.shape
+    cols = np.ascontiguousarray(np.asarray(mapP_cols).T, dtype=np.int64)      # [k][j]
+    plan = SseShardPlan()
+    mp = np.empty(N_f * n_loc, dtype=np.int64)
+    send = np.empty(N_f * n_loc, dtype=np.int64)
+    rc = lib.sse_shard_plan_build(cols.ctypes.data_as(c_i64_p), N_f, N_e_global, rank, world,
+                                  C.byref(plan), mp.ctypes.data_as(c_i64_p),
+                                  send.ctypes.data_as(c_i64_p))
+    if rc != 0:
+        raise RuntimeError("sse_shard_plan_build failed: " + lib.sse_last_error().decode())
+    return plan, mp.reshape(n_loc, N_f).T, send[:plan.n_send].copy()
 
 
 def measure_dmma_peak(device: int = 0) -> float:
@@ -223,9 +280,12 @@ class DeviceResidual:
     """Owns an ``sse_handle``: device-resident operators, geometry, state and scratch."""
 
     def __init__(self, solver, device: int = 0, mapP: Optional[np.ndarray] = None,
-                 n_halo: int = 0, elements: Optional[np.ndarray] = None):
+                 n_halo: int = 0, elements: Optional[np.ndarray] = None, shard=None):
         """``elements``: optional index array selecting a shard of the mesh (multi-GPU);
-        ``mapP``: (N_f, N_e_local) local connectivity override with halo slots."""
+        ``mapP``: (N_f, N_e_local) local connectivity override with halo slots.
+        ``shard`` = (rank, world, nccl_id, N_e_global): create the handle through
+        ``sse_shard_create`` -- ``mapP`` then holds the columns of the GLOBAL connectivity of this
+        rank's elements, and the partition, the halo and the NCCL exchange live in the library."""
         self.lib = load_library()
         sd = solver.spatial_discretization
         ra = sd.reference_approximation
@@ -329,10 +389,25 @@ class DeviceResidual:
             mapP = sd.mesh.mapP
         mp = np.ascontiguousarray(np.asarray(mapP).T, dtype=np.int64)      # [k][j]
         h = C.c_void_p()
-        rc = self.lib.sse_create(C.byref(cfg), C.byref(ops), C.byref(geo),
-                                 mp.ctypes.data_as(c_i64_p), C.byref(h))
-        if rc != 0:
-            raise RuntimeError("sse_create failed: " + self.lib.sse_last_error().decode())
+        self.shard = None
+        if shard is not None:
+            rank, world, nccl_id, N_e_global = shard
+            cfg.N_e, cfg.N_halo = N_e_global, 0
+            sh = C.c_void_p()
+            idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+            rc = self.lib.sse_shard_create(C.byref(cfg), C.byref(ops), C.byref(geo),
+                                           mp.ctypes.data_as(c_i64_p), rank, world, idbuf,
+                                           C.byref(sh))
+            if rc != 0:
+                raise RuntimeError("sse_shard_create failed: " +
+                                   self.lib.sse_last_error().decode())
+            self.shard = sh
+            h = C.c_void_p(self.lib.sse_shard_handle(sh))
+        else:
+            rc = self.lib.sse_create(C.byref(cfg), C.byref(ops), C.byref(geo),
+                                     mp.ctypes.data_as(c_i64_p), C.byref(h))
+            if rc != 0:
+                raise RuntimeError("sse_create failed: " + self.lib.sse_last_error().decode())
         self.h = h
         self._keep = []   # everything was copied to the device
 
@@ -342,9 +417,42 @@ class DeviceResidual:
             raise RuntimeError(f"{what} failed: " + self.lib.sse_last_error().decode())
 
     def close(self):
+        if getattr(self, "shard", None):
+            self.lib.sse_shard_destroy(self.shard)      # destroys the handle as well
+            self.shard = None
+            self.h = None
         if getattr(self, "h", None):
             self.lib.sse_destroy(self.h)
             self.h = None
+
+    # ------------------------------------------------------------------ sharded (sse_shard_*)
+    def shard_plan(self):
+        plan = SseShardPlan()
+        self._check(self.lib.sse_shard_get_plan(self.shard, C.byref(plan)), "sse_shard_get_plan")
+        return plan
+
+    def shard_residual(self, u: Optional[np.ndarray] = None, dudt: Optional[np.ndarray] = None):
+        """Device-resident (no arguments) or host-buffer residual of the shard."""
+        if u is None:
+            self._check(self.lib.sse_shard_residual(self.shard, None, None, 0.0, 1),
+                        "sse_shard_residual")
+            return
+        assert u.shape == self.shape and dudt.shape == self.shape
+        assert u.flags.c_contiguous and dudt.flags.c_contiguous
+        self._check(self.lib.sse_shard_residual(self.shard, u.ctypes.data, dudt.ctypes.data, 0.0,
+                                                0), "sse_shard_residual")
+
+    def shard_time_residual(self, reps: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.sse_shard_time_residual(self.shard, reps, C.byref(ms)),
+                    "sse_shard_time_residual")
+        return float(ms.value)
+
+    def shard_rk_step_ck54(self, dt: float):
+        self._check(self.lib.sse_shard_rk_step_ck54(self.shard, dt), "sse_shard_rk_step_ck54")
+
+    def shard_sync(self):
+        self._check(self.lib.sse_shard_sync(self.shard), "sse_shard_sync")
 
     def __del__(self):
         try:

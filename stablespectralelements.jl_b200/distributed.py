@@ -118,16 +118,47 @@ class _DevBuf:
 class DistributedResidual:
     """Residual of one element shard on one GPU (world = 1: the whole mesh, no exchange)."""
 
-    def __init__(self, solver, rank: int = 0, world: int = 1, device: int = 0):
+    def __init__(self, solver, rank: int = 0, world: int = 1, device: int = 0,
+                 backend: Optional[str] = None, nccl_id: Optional[bytes] = None):
+        """``backend``: "library" (default at world > 1): partition, halo and the NCCL exchange
+        live behind the C ABI (``sse_shard_create`` / ``sse_shard_residual``; the 128-byte NCCL id
+        is taken from ``nccl_id`` or broadcast from rank 0 over torch.distributed);
+        "python": the flow generator below drives the exchange with torch.distributed P2P (what
+        the sharded-emulation tests run, with device copies as the transport)."""
+        import os
         from .device import DeviceResidual
         self.solver, self.rank, self.world = solver, rank, world
         sd = solver.spatial_discretization
         self.dim = sd.reference_approximation.dim
         self.second_order = solver.law_desc["kind"] in ("advection_diffusion", "viscous_burgers")
+        self.backend = backend or os.environ.get("SSE_B200_SHARD_BACKEND", "library")
         if world == 1:
             self.part = None
+            self.backend = "single"
             self.elements = np.arange(sd.N_e)
             self.dev = DeviceResidual(solver, device=device)
+        elif self.backend == "library":
+            from .device import nccl_unique_id
+            N_e_global = sd.mesh.mapP.shape[1]
+            start, stop = element_ranges(N_e_global, world)[rank]
+            self.elements = np.arange(start, stop)
+            if nccl_id is None:
+                import torch.distributed as dist
+                box = [nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                nccl_id = box[0]
+            cols = sd.mesh.mapP[:, start:stop]
+            local = sd.mesh.elem_start is not None
+            if local and (sd.mesh.elem_start != start or sd.N_e != stop - start):
+                raise ValueError("mesh shard does not match this rank's element range")
+            self.dev = DeviceResidual(solver, device=device, mapP=cols,
+                                      elements=None if local else self.elements,
+                                      shard=(rank, world, nccl_id, N_e_global))
+            pl = self.dev.shard_plan()
+            self.part = Partition(rank, world, start, stop, None, int(pl.n_halo), None,
+                                  {int(pl.peers[q]): int(pl.send_counts[q]) for q in range(pl.n_peers)},
+                                  {int(pl.peers[q]): int(pl.recv_counts[q]) for q in range(pl.n_peers)},
+                                  (int(pl.k_lo), int(pl.k_hi)))
         else:
             import torch
             self.torch = torch
@@ -313,7 +344,9 @@ class DistributedResidual:
 
     def residual(self):
         """One residual of the device-resident state (dudt stays on the device)."""
-        if self.world == 1:
+        if self.backend == "library":
+            self.dev.shard_residual()
+        elif self.world == 1:
             self.dev.nodal_values()
             self.dev.time_derivative()
         else:
@@ -324,6 +357,9 @@ class DistributedResidual:
         """Public-API path with host buffers for this shard (H2D + residual + D2H)."""
         if self.world == 1:
             self.dev.residual_host(u, dudt)
+            return
+        if self.backend == "library":
+            self.dev.shard_residual(u, dudt)
             return
         import os
         if os.environ.get("SSE_B200_SHARD_PIPELINE") == "1" and not self.second_order:
@@ -342,6 +378,9 @@ class DistributedResidual:
         import os
         if self.world == 1:
             return "sse_residual(where=HOST): chunked H2D / loop A / loop B / D2H pipeline"
+        if self.backend == "library":
+            return ("sse_shard_residual(where=HOST): chunked H2D + loop A, NCCL exchange || interior "
+                    "loop B, boundary loop B, D2H by ranges")
         if os.environ.get("SSE_B200_SHARD_PIPELINE") == "1" and not self.second_order:
             return "interleaved: boundary upload -> exchange || interior upload + loops A, B + D2H"
         return "upload + loop A, exchange || interior loop B, boundary loop B, D2H by ranges"
@@ -350,6 +389,8 @@ class DistributedResidual:
         """Milliseconds for ``steps`` residuals, CUDA events on the launching stream."""
         if self.world == 1:
             return self.dev.time_residual(steps, split=False)[0]
+        if self.backend == "library":
+            return self.dev.shard_time_residual(steps)
         torch = self.torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -376,7 +417,10 @@ class DistributedResidual:
         return self.dev.kernel_launches()
 
     def sync(self):
-        self.dev.sync()
+        if self.backend == "library":
+            self.dev.shard_sync()
+        else:
+            self.dev.sync()
 
     def close(self):
         self.dev.close()

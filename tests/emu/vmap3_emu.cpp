@@ -4,7 +4,7 @@
 #define SSE_HOST_EMU 1
 #include <cmath>
 #include <cstring>
-#include "../../stablespectralelements.jl_b200/csrc/vmap3.cuh"
+#include "../../stablespectralelements.jl_b200/csrc/vmap3b.cuh"
 
 using namespace sse;
 
@@ -40,5 +40,41 @@ extern "C" int vmap3_emu(int n1, int nc, int e, int transpose, const double* wA,
 #define CASE(N, C, EE) if (n1 == N && nc == C && e == EE) { run<N, C, EE>(transpose, T, src, dst, Z, nthr); return 0; }
   CASE(5, 5, 1) CASE(5, 1, 1) CASE(5, 4, 1) CASE(4, 5, 2) CASE(4, 1, 2) CASE(3, 5, 4) CASE(3, 1, 4)
   CASE(4, 4, 1) CASE(3, 4, 1)
+  return -1;
+}
+
+
+// ---- batched, register-tiled engine (csrc/vmap3b.cuh): X [G][NCOL][n^3], M [G][NCOL][NP], Z scratch
+template <int N1, int NCOL, int G>
+static void run_b(int mode, V3Tab T, double* X, double* M, double* Z, int nthr) {
+#define STAGE(call) for (int t = 0; t < nthr; ++t) call
+  if (mode == 0) {            // X = V M
+    STAGE((vb_stageC<N1, NCOL, G, false>(t, nthr, T, M, Z)));
+    STAGE((vb_stageB<N1, NCOL, G, false>(t, nthr, Z, X)));
+    STAGE((vb_stageA<N1, NCOL, G, false>(t, nthr, X)));
+  } else if (mode == 1) {     // M = V^T X (X destroyed)
+    STAGE((vb_stageA<N1, NCOL, G, true>(t, nthr, X)));
+    STAGE((vb_stageB<N1, NCOL, G, true>(t, nthr, Z, X)));
+    STAGE((vb_stageC<N1, NCOL, G, true>(t, nthr, T, M, Z)));
+  } else {                    // X <- V V^T X in place
+    STAGE((vb_stageA<N1, NCOL, G, true>(t, nthr, X)));
+    STAGE((vb_stageB<N1, NCOL, G, true>(t, nthr, Z, X)));
+    STAGE((vb_stageK<N1, NCOL, G>(t, nthr, T, Z)));
+    STAGE((vb_stageB<N1, NCOL, G, false>(t, nthr, Z, X)));
+    STAGE((vb_stageA<N1, NCOL, G, false>(t, nthr, X)));
+  }
+#undef STAGE
+}
+
+extern "C" int vmap3b_emu(int n1, int ncol, int g, int mode, const double* wA, const double* wB,
+                          const double* wC, const int* sigma, double* X, double* M, double* Z,
+                          int nthr) {
+  std::memcpy(c_wA[n1 - 3], wA, sizeof(double) * n1 * n1);
+  std::memcpy(c_wB[n1 - 3], wB, sizeof(double) * n1 * n1 * n1);
+  V3HostTables ht;
+  if (!v3_build_tables(n1, sigma, wC, ht)) return -2;
+  V3Tab T{wC, ht.wCt.data(), ht.pairtab.data(), ht.modetab.data(), ht.wK.data()};
+#define CASEB(N, C, GG) if (n1 == N && ncol == C && g == GG) { run_b<N, C, GG>(mode, T, X, M, Z, nthr); return 0; }
+  CASEB(5, 5, 4) CASEB(5, 5, 5) CASEB(5, 5, 1) CASEB(4, 5, 6) CASEB(3, 5, 8) CASEB(5, 4, 3) CASEB(4, 2, 5)
   return -1;
 }

@@ -187,3 +187,33 @@ def test_partition_properties():
         assert p.mapP_local.max() < N_f * (p.stop - p.start) + p.n_halo
         halo = p.mapP_local[p.mapP_local >= N_f * (p.stop - p.start)]
         assert len(np.unique(halo)) == len(halo) == p.n_halo
+
+
+@pytest.mark.parametrize("builder", [("euler_tet_case", dict(p=2, M=3, lazy=True)),
+                                     ("advection_diffusion_case", dict(d=1, p=2, M=7, lazy=True)),
+                                     ("euler_tri_case", dict(p=2, M=4, lazy=True))])
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_library_partition_matches_the_python_partitioner(builder, world):
+    """sse_shard_plan_build (C ABI, pure host arithmetic -- what a Julia rank calls through
+    sse_shard_create) against the NumPy ``partition`` every sharded test above is built on: same
+    ranges, halo numbering, send lists, peer counts and interior range."""
+    from sse_b200 import device as dev
+    import __graft_entry__ as ge
+    ge.build()
+    solver, _ = getattr(cases, builder[0])(**builder[1])
+    mapP = solver.spatial_discretization.mesh.mapP
+    N_f, N_e = mapP.shape
+    for rank in range(world):
+        part = partition(mapP, rank, world)
+        plan, mp_local, send = dev.shard_plan(mapP[:, part.start:part.stop], N_e, rank, world)
+        assert (plan.start, plan.stop) == (part.start, part.stop)
+        assert plan.n_halo == part.n_halo and plan.n_send == len(part.send_idx)
+        assert np.array_equal(mp_local, part.mapP_local)
+        assert np.array_equal(send, part.send_idx)
+        peers = [int(plan.peers[q]) for q in range(plan.n_peers)]
+        assert peers == sorted(part.send_counts)
+        assert [int(plan.send_counts[q]) for q in range(plan.n_peers)] == \
+            [part.send_counts[p] for p in peers]
+        assert [int(plan.recv_counts[q]) for q in range(plan.n_peers)] == \
+            [part.recv_counts[p] for p in peers]
+        assert (plan.k_lo, plan.k_hi) == tuple(part.interior)

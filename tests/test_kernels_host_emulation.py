@@ -49,10 +49,10 @@ CASES = {
     # north-star path: specialised loop A / loop B kernels on collapsed tetrahedra
     "euler3d_tet_p4_warp_lf": (lambda: cases.euler_tet_case(p=4, M=2, lazy=True, warp=True,
                                                             ic="periodic"),
-                               ["k_nodal_tensorILi3ELi5E", "k_fluxdiff_tensorILi3ELi5E"]),
+                               ["k_nodal_tensorILi3ELi5E", "k_fluxdiff_nodalILi3ELi5E", "k_project_tetILi5E"]),
     "euler3d_tet_p3_warp_ec": (lambda: cases.euler_tet_case(p=3, M=2, lazy=True, warp=True,
                                                             interface="ec", ic="periodic"),
-                               ["k_nodal_tensorILi3ELi4E", "k_fluxdiff_tensorILi3ELi4E"]),
+                               ["k_nodal_tensorILi3ELi4E", "k_fluxdiff_nodalILi3ELi4E", "k_project_tetILi4E"]),
     "euler3d_tet_p2_nodal": (lambda: cases.euler_tet_case(p=2, M=2, lazy=True, approx="nodal"),
                              ["k_nodal_", "k_fluxdiff"]),
     "euler2d_tri_p4_lf": (lambda: cases.euler_tri_case(p=4, M=3, lazy=True),
@@ -123,6 +123,28 @@ def test_emulated_kernels_match_oracle(emu_lib, name):
             assert k in launched, (k, launched)
         ref = oc.semi_discrete_residual(oracle_problem(solver), u)
         assert np.all(np.isfinite(dudt))
+        assert _rel(dudt, ref) < 1e-12
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("name,p", [("euler3d_tet_p4_warp_lf", 4), ("euler3d_tet_p3_warp_ec", 3)])
+def test_one_element_tet_kernels_in_emulation(emu_lib, name, p, monkeypatch):
+    """SSE_B200_TET_ENGINE=0: loop B with the projection as its tail (the A/B reference of the
+    batched projection kernel, and the path of the 2-D and nodal configurations)."""
+    monkeypatch.setenv("SSE_B200_TET_ENGINE", "0")
+    build, _ = CASES[name]
+    solver, u0 = build()
+    u = cases.rough_state(solver, u0, seed=1)
+    d = dev.DeviceResidual(solver)
+    try:
+        emu_lib.emu_launch_log()
+        dudt = np.full_like(u, np.nan)
+        d.residual_host(u, dudt)
+        launched = emu_lib.emu_launch_log().decode()
+        assert f"k_nodal_tensorILi3ELi{p + 1}E" in launched
+        assert f"k_fluxdiff_tensorILi3ELi{p + 1}E" in launched
+        ref = oc.semi_discrete_residual(oracle_problem(solver), u)
         assert _rel(dudt, ref) < 1e-12
     finally:
         d.close()

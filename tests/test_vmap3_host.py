@@ -64,3 +64,42 @@ def test_vmap3_stages_match_dense_V(emu, p, nc, e, nthr):
     assert rc == 0
     ref = y2 @ Vd @ Vd.T
     assert np.max(np.abs(src.reshape(e * nc, Nq) - ref)) < 1e-13 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("p,ncol,g", [(4, 5, 4), (4, 5, 5), (4, 5, 1), (3, 5, 6), (2, 5, 8),
+                                      (4, 4, 3), (3, 2, 5)])
+@pytest.mark.parametrize("nthr", [128, 96])
+def test_batched_engine_matches_dense_V(emu, p, ncol, g, nthr):
+    """csrc/vmap3b.cuh (all columns of a tensor line / b1 group / pair per work item, several
+    elements per CTA): V, V^T and the fused V V^T against the dense Vandermonde matrix."""
+    ra = make_reference_approximation(ModalTensor(p), Tet())
+    V = ra.V
+    n = p + 1
+    Vd = V.to_dense()
+    Nq, Np = Vd.shape
+    sig = np.ascontiguousarray(V.sigma_i, dtype=np.int32)
+    A = np.ascontiguousarray(V.A); B = np.ascontiguousarray(V.B); C = np.ascontiguousarray(V.C)
+    rng = np.random.default_rng(p * 100 + ncol * 10 + g)
+    ZS = n * n * (n + 1) // 2
+    cols = g * ncol
+
+    def call(mode, X, M):
+        Z = np.full(g * (ncol * ZS + 16), np.nan)
+        rc = emu.vmap3b_emu(n, ncol, g, mode, _ptr(A), _ptr(B), _ptr(C), _ptr(sig, ctypes.c_int),
+                            _ptr(X), _ptr(M), _ptr(Z), nthr)
+        assert rc == 0
+
+    m = rng.standard_normal((cols, Np))
+    X = np.full(cols * Nq, np.nan); M = m.copy().ravel()
+    call(0, X, M)
+    ref = m @ Vd.T
+    assert np.max(np.abs(X.reshape(cols, Nq) - ref)) < 1e-13 * np.max(np.abs(ref))
+    x = rng.standard_normal((cols, Nq))
+    X = x.copy().ravel(); M = np.full(cols * Np, np.nan)
+    call(1, X, M)
+    ref = x @ Vd
+    assert np.max(np.abs(M.reshape(cols, Np) - ref)) < 1e-13 * np.max(np.abs(ref))
+    X = x.copy().ravel(); M = np.zeros(1)
+    call(2, X, M)
+    ref = x @ Vd @ Vd.T
+    assert np.max(np.abs(X.reshape(cols, Nq) - ref)) < 1e-13 * np.max(np.abs(ref))

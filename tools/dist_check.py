@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 import numpy as np
 import torch
 import torch.distributed as dist
-import cases
+from sse_b200 import problems as cases
 import sse_oracle as oc
 from bridge import oracle_problem
 from sse_b200.distributed import DistributedResidual
@@ -24,22 +24,28 @@ for name, (solver, u0) in {
         "advdiff2d_p3_br1": cases.advection_diffusion_case(d=2, p=3, M=8, lazy=True)}.items():
     u = cases.rough_state(solver, u0, seed=3)
     ref = oc.semi_discrete_residual(oracle_problem(solver), u)
-    d = DistributedResidual(solver, rank=rank, world=world, device=lr)
-    d.set_state(u[d.elements])
-    for _ in range(2):
-        d.residual()
-    out = d.get_dudt()
-    err = float(np.max(np.abs(out - ref[d.elements])) / np.max(np.abs(ref)))
-    u_h = np.ascontiguousarray(u[d.elements]); du_h = np.empty_like(u_h)
-    d.residual_host(u_h, du_h)
-    err2 = float(np.max(np.abs(du_h - ref[d.elements])) / np.max(np.abs(ref)))
-    t = torch.tensor([max(err, err2)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(f"{name}: world={world} max rel err over ranks = {t.item():.3e} "
-              f"(interior range {d.part.interior if d.part else None}, halo {d.part.n_halo if d.part else 0})", flush=True)
-    worst = max(worst, t.item())
-    d.close()
+    # "library": sse_shard_create / sse_shard_residual (partition + NCCL inside the C ABI);
+    # "python": the torch.distributed P2P flow of distributed.py
+    for backend in ("library", "python"):
+        d = DistributedResidual(solver, rank=rank, world=world, device=lr, backend=backend)
+        d.set_state(u[d.elements])
+        for _ in range(2):
+            d.residual()
+        d.sync()
+        out = d.get_dudt()
+        err = float(np.max(np.abs(out - ref[d.elements])) / np.max(np.abs(ref)))
+        u_h = np.ascontiguousarray(u[d.elements]); du_h = np.full_like(u_h, np.nan)
+        for _ in range(2):
+            d.residual_host(u_h, du_h)
+        err2 = float(np.max(np.abs(du_h - ref[d.elements])) / np.max(np.abs(ref)))
+        same = bool(np.array_equal(du_h, out))
+        t = torch.tensor([max(err, err2)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"{name} [{backend}]: world={world} max rel err over ranks = {t.item():.3e}, host path "
+                  f"bitwise = {same} (interior {d.part.interior}, halo {d.part.n_halo})", flush=True)
+        worst = max(worst, t.item())
+        d.close()
 dist.barrier()
 dist.destroy_process_group()
 assert worst < 1e-12, worst
