@@ -255,9 +255,32 @@ def measure(builder, D, local_rank, steps, warmup, device_geometry=False, e2e=Tr
             dres.residual_host(u_np, du_np)
         barrier()
         te = D.max((time.perf_counter() - t0) / ke)
+        # the floor of the host-buffer call: the same bytes over PCIe, both directions at once, all
+        # ranks together, no kernels (e2e >= max(this, the device-resident step))
+        dv = torch.device("cuda", local_rank)
+        d_in = torch.empty(n_loc, dtype=torch.float64, device=dv)
+        d_out = torch.zeros(n_loc, dtype=torch.float64, device=dv)
+        s_up, s_dn = torch.cuda.Stream(dv), torch.cuda.Stream(dv)
+        tp = []
+        for rep in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                d_in.copy_(u_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                du_host.copy_(d_out, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+            tp.append(D.max(time.perf_counter() - t0))
+        du_np[...] = 0.0
+        dres.residual_host(u_np, du_np)          # restore dudt for the digest check below
+        t_pcie = min(tp[1:])
+        del d_in, d_out
         out["e2e"] = {"value": dof / te, "unit": "DOF/s", "h2d_bytes_per_step": 8 * dof,
                       "d2h_bytes_per_step": 8 * dof, "ms_per_step": te * 1e3,
-                      "flow": dres.host_flow_name()}
+                      "flow": dres.host_flow_name(),
+                      "pcie_floor_ms": t_pcie * 1e3,
+                      "pcie_GBps_each_way_per_gpu": 8 * n_loc / t_pcie / 1e9}
         if functionals:   # the host-buffer path must give the very same dudt
             start = int(dres.elements[0]) * N_c * N_p
             parts = D.gather(digest(du_np, start))

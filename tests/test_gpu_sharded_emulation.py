@@ -30,7 +30,8 @@ def _local_exchange(shards, width):
 def _run_sharded(solver, u, world, shard_cls=None):
     from sse_b200.distributed import DistributedResidual
     shard_cls = shard_cls or DistributedResidual
-    shards = [shard_cls(solver, rank=r, world=world, device=0) for r in range(world)]
+    shards = [shard_cls(solver, rank=r, world=world, device=0, backend="python")
+              for r in range(world)]
     try:
         for sh in shards:
             sh.set_state(np.ascontiguousarray(u[sh.elements]))

@@ -73,7 +73,8 @@ def test_interleaved_host_flow_two_shards_on_one_gpu():
         whole.residual_host(u, ref)
     finally:
         whole.close()
-    shards = [DistributedResidual(solver, rank=r, world=2, device=0) for r in range(2)]
+    shards = [DistributedResidual(solver, rank=r, world=2, device=0, backend="python")
+              for r in range(2)]
     try:
         for sh in shards:
             sh.dev.set_copy_streams(True)

@@ -368,7 +368,8 @@ def test_interleaved_host_flow_in_emulation(emu_lib, world):
         whole.residual_host(u, ref)
     finally:
         whole.close()
-    shards = [Shard(solver, rank=r, world=world, device=0) for r in range(world)]
+    shards = [Shard(solver, rank=r, world=world, device=0, backend="python")
+              for r in range(world)]
     try:
         import test_gpu_sharded_emulation as ts
         us = [np.ascontiguousarray(u[sh.elements]) for sh in shards]
