@@ -348,6 +348,13 @@ def secondary_single_gpu(reps=10):
         lambda: problems.euler_tri_case(p=4, M=256, lazy=False),
         8 * (2 * 60 + 60 + 2 * 25 + 100 + 30 + 60 + 120) + 4 * 15,
         "k_nodal_tensor<2,5,Euler> + k_fluxdiff_tensor<2,5,Euler>")
+    # the reference's own 3-D Euler test (NodalTensor Hex p=4, EC interface flux,
+    # test/euler_3d.jl, M = 2) scaled up to 64^3 / 8 = 32 768 hexahedra; FP64-bound like config 4:
+    # 750 pair fluxes + 150 interface fluxes per element, ~155 kflop, 2 x 5000 + 11 000 B
+    run("hex: euler3d NodalTensor Hex p4 flux differencing (diagonal-E) M=32",
+        lambda: problems.euler_hex_case(p=4, M=32, lazy=False),
+        8 * (2 * 625 + 625 + 1125 + 125 + 150 + 450 + 2 * 750) + 4 * 150,
+        "k_nodal_values<3,Euler> + k_fluxdiff_tensor<3,5,Euler,non-collapsed>")
     for p in range(2, 9):
         n1 = p + 1
         Np, Nq, Nf = n1 * (n1 + 1) // 2, n1 * n1, 3 * n1

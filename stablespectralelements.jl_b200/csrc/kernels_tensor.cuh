@@ -925,8 +925,10 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
     }
     return;
   }
-  // ---- phases 3/4: facet correction (ELL rows of C = R^T B), exchanged in two halves
-  if (!T.r_is_selection) {
+  // ---- phases 3/4: facet correction (ELL rows of C = R^T B), exchanged in two halves.  Only the
+  // collapsed simplices have one; the non-collapsed instantiations are the diagonal-E schemes on
+  // quadrilaterals / hexahedra (LGL collocation, R a selection: flux_differencing_form.jl:171-187)
+  if constexpr (COLLAPSED) if (!T.r_is_selection) {
 #pragma unroll
     for (int half = 0; half < Cf::NPART; ++half) {
       __syncthreads();   // previous users of sX (pair buffers / previous part) are done
@@ -1030,13 +1032,22 @@ __device__ __forceinline__ void fluxdiff_tensor_body(
   __syncthreads();
   // ---- phase 5: r_q -= R^T f_f (ELL), then hand r_q to the modal projection
   if (active) {
+    if constexpr (COLLAPSED) {
 #pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      const int j = canon_facet_node<DIM, N1>(kk, ia1, ia2, ia3);
-      const double rv = __ldg(F.Rv + kk * NQ + i);
-      const double* ff = sFf + e * NC * NF + j;
+      for (int kk = 0; kk < KC; ++kk) {
+        const int j = canon_facet_node<DIM, N1>(kk, ia1, ia2, ia3);
+        const double rv = __ldg(F.Rv + kk * NQ + i);
+        const double* ff = sFf + e * NC * NF + j;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
+        for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
+      }
+    } else {   // selection R: the node lies on 0..DIM faces (rows of R^T, CSR)
+      for (int en = __ldg(T.Rt_rp + i); en < __ldg(T.Rt_rp + i + 1); ++en) {
+        const double rv = __ldg(T.Rt_v + en);
+        const double* ff = sFf + e * NC * NF + __ldg(T.Rt_ci + en);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) r[c] = fma(-rv, ff[c * NF], r[c]);
+      }
     }
     if constexpr (PART == 3) {   // the projection runs as its own batched kernel (k_project_tet)
       if (k0 + e < G.N_e) {

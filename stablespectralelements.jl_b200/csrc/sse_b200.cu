@@ -160,7 +160,9 @@ static int fast_a_key(int dim, int n1, int law) {
   return 0;
 }
 static int fast_b_key(int dim, int n1, int law, int collapsed, int kc) {
-  if (law != LAW_EULER || !collapsed || n1 < 3 || n1 > 5) return 0;
+  if (law != LAW_EULER || n1 < 3 || n1 > 5) return 0;
+  if (!collapsed)   // kc = -1 marks the diagonal-E selection path (quadrilaterals / hexahedra)
+    return (kc == -1 && n1 >= 4 && (dim == 2 || dim == 3)) ? 1000 + dim * 100 + n1 : 0;
   if (dim == 3 && kc == 3 + n1) return 300 + n1;
   if (dim == 2 && kc == 3) return 200 + n1;
   return 0;
@@ -513,9 +515,19 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       bool uniform = true;
       for (int i = 0; i < Nq; ++i) uniform = uniform && (Rt.rp[i + 1] - Rt.rp[i] == kc);
       const bool collapsed = !Gref.empty();
-      bool ok = d >= 2 && n1 >= 2 && (int)nd1 == Nq && uniform && kc > 0 && !cfg->r_is_selection &&
-                !ops->Minv && h->r_ap && Nf < 65536 &&
+      // diagonal-E collocation on quadrilaterals / hexahedra: identity V, selection R (no facet
+      // correction, flux_differencing_form.jl:171-187), diagonal mass solve
+      const bool sel_path = cfg->r_is_selection && !collapsed && cfg->v_kind == SSE_V_IDENTITY &&
+                            cfg->mass_solver == SSE_MASS_DIAGONAL &&
+                            cfg->form == SSE_FORM_FLUX_DIFFERENCING;
+      size_t npf_sel = 1;
+      for (int m = 0; m + 1 < d; ++m) npf_sel *= (size_t)std::max(n1, 1);
+      bool ok = d >= 2 && n1 >= 2 && (int)nd1 == Nq &&
+                (sel_path ? Nf == (int)(2 * d * npf_sel)
+                          : (uniform && kc > 0 && !cfg->r_is_selection && h->r_ap)) &&
+                !ops->Minv && Nf < 65536 &&
                 (cfg->mass_solver == SSE_MASS_WEIGHT_ADJUSTED || cfg->mass_solver == SSE_MASS_DIAGONAL);
+      if (sel_path) kc = 0;
       std::vector<int> stride(d, 1);
       for (int l = 0; l < d; ++l)
         for (int q = l + 1; q < d; ++q) stride[l] *= std::max(n1, 1);
@@ -551,10 +563,11 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
         // canonical facet layout of the collapsed tensor-product simplices (FastTables): ELL slot
         // -> facet node by formula, and the rows of R as the tensor lines / collapsed-face blocks
         // the specialised kernels sum over
-        bool slots_ok = collapsed && (d == 2 || d == 3) && cfg->num_faces == d + 1 &&
+        bool slots_ok = sel_path;
+        if (!sel_path) slots_ok = collapsed && (d == 2 || d == 3) && cfg->num_faces == d + 1 &&
                         cfg->num_faces * d <= 12 && ops->n_ref != nullptr &&
                         kc == (d == 3 ? 3 + n1 : 3);
-        {
+        if (!sel_path) {
           const int npf = d == 3 ? n1 * n1 : n1;
           slots_ok = slots_ok && Nf == (d == 3 ? 4 : 3) * npf;
           for (int i = 0; i < Nq && slots_ok; ++i) {
@@ -575,10 +588,10 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
             slots_ok = slots_ok && cnt == (block_face ? n1 * n1 : n1);
           }
         }
-        if (slots_ok)
+        if (slots_ok && !sel_path)
           for (int q = 0; q < cfg->num_faces * d; ++q) h->F.nref[q] = 0.5 * ops->n_ref[q];   // ½ n_ref
         ok = ok && (slots_ok || cfg->form != SSE_FORM_FLUX_DIFFERENCING);
-        h->n1 = n1; h->kc = kc; h->collapsed = collapsed;
+        h->n1 = n1; h->kc = sel_path ? -1 : kc; h->collapsed = collapsed;
         h->fast_std = (cfg->form == SSE_FORM_STANDARD) ? 1 : 0;
       }
       if (ok && cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
@@ -728,8 +741,9 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf + wtmp * Nc);
   };
   auto smem_b = [&](int E) -> size_t {
-    if (cfg->strategy == SSE_PHYSICAL_OPERATOR)
-      return sizeof(double) * (size_t)E * d * Nc * ((size_t)2 * Nq + Nf + Np + wtmp);
+    if (cfg->strategy == SSE_PHYSICAL_OPERATOR)   // + the staged operators VOL[k], FAC[k]
+      return sizeof(double) * (size_t)E * (d * Nc * ((size_t)2 * Nq + Nf + Np + wtmp) +
+                                           (size_t)d * Np * Nq + (size_t)Np * Nf);
     if (cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
       size_t sD = std::max((size_t)T.nnzRt * Nc, wtmp * Nc);
       return sizeof(double) * (size_t)E * ((size_t)NS * Nq + (size_t)d * d * Nq + (size_t)NS * Nf +

@@ -35,7 +35,7 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
       return 0;
     }
   }
-  if (h->split_b) {
+  if constexpr (COLLAPSED) if (h->split_b) {
     const size_t smem_v = Cf::bytes_volume();
     CU(cudaFuncSetAttribute(k_fluxdiff_volume<DIM, N1, LAW, COLLAPSED, KC>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
@@ -65,6 +65,9 @@ int sse_launch_fluxdiff_fast_2d(sse_handle* h, double* dudt_dev, const RK& rk) {
     case 203: return launch_b_fast<2, 3, LAW_EULER, true, 3>(h, dudt_dev, rk);
     case 204: return launch_b_fast<2, 4, LAW_EULER, true, 3>(h, dudt_dev, rk);
     case 205: return launch_b_fast<2, 5, LAW_EULER, true, 3>(h, dudt_dev, rk);
+    // diagonal-E collocation on quadrilaterals (NodalTensor LGL, R a selection)
+    case 1204: return launch_b_fast<2, 4, LAW_EULER, false, 1>(h, dudt_dev, rk);
+    case 1205: return launch_b_fast<2, 5, LAW_EULER, false, 1>(h, dudt_dev, rk);
     default: return fail("no specialised 2-D loop-B kernel for key %d", h->fast_b);
   }
 }
@@ -77,6 +80,9 @@ int sse_launch_fluxdiff_fast_3d(sse_handle* h, double* dudt_dev, const RK& rk) {
     case 303: return launch_b_fast<3, 3, LAW_EULER, true, 6>(h, dudt_dev, rk);
     case 304: return launch_b_fast<3, 4, LAW_EULER, true, 7>(h, dudt_dev, rk);
     case 305: return launch_b_fast<3, 5, LAW_EULER, true, 8>(h, dudt_dev, rk);
+    // diagonal-E collocation on hexahedra (NodalTensor LGL, R a selection)
+    case 1304: return launch_b_fast<3, 4, LAW_EULER, false, 1>(h, dudt_dev, rk);
+    case 1305: return launch_b_fast<3, 5, LAW_EULER, false, 1>(h, dudt_dev, rk);
     default: return fail("no specialised 3-D loop-B kernel for key %d", h->fast_b);
   }
 }

@@ -68,7 +68,7 @@ CASES = {
     "adv2d_tri_p4": (lambda: cases.advection_tri_case(p=4, M=3, lazy=True), ["k_standard"]),
     "burgers2d_tri_p3_ec": (lambda: cases.burgers_tri_case(p=3, M=3, lazy=True), ["k_fluxdiff"]),
     "euler3d_hex_nodal_p3_ec": (lambda: cases.euler_hex_case(p=3, M=2, lazy=True),
-                                ["k_nodal_values", "k_fluxdiffILi3E"]),
+                                ["k_nodal_values", "k_fluxdiff_tensorILi3ELi4ELi2ELb0E"]),
     # physical operators, BR1 (two k_physical launches: auxiliary_variable!, time_derivative!)
     "advdiff1d_p4": (lambda: cases.advection_diffusion_case(d=1, p=4, M=4, lazy=True),
                      ["k_physicalILi1E"]),
