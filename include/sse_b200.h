@@ -205,6 +205,10 @@ int sse_measure_fp64_peak(int device, double* tflops);
 /* The same for FP64 tensor-core instructions (mma.sync m8n8k4, dense 8x8x4 tiles): the measured
  * basis of the decision NOT to use DMMA for the (p+1)-wide contractions. */
 int sse_measure_dmma_peak(int device, double* tflops);
+/* y[i] = log(x[i]) (which = 0) or exp(x[i]) (which = 1) through the device functions the
+ * entropy-variable maps use (euler_navierstokes.jl:100-131 evaluates them with Base.log / exp);
+ * host arrays; a test hook for their accuracy. */
+int sse_probe_elementary(int device, int which, const double* x, double* y, int64_t n);
 int64_t sse_kernel_launches(sse_handle* h);             /* kernels launched so far          */
 int64_t sse_device_bytes(sse_handle* h);                /* device memory owned by the handle */
 

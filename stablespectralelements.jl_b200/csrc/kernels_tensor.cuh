@@ -238,6 +238,37 @@ __device__ __noinline__ void apply_VtV_t(const VTab T, double* __restrict__ x,
   __syncthreads();
 }
 
+// x <- V V^T diag(sc) V V^T x in place (3-D warped product): the entropy projection with the
+// weight-adjusted mass inverse, V M^-1 V^T with M^-1 = V^T (W/J) V.  Nine stages instead of the
+// eleven of two apply_VtV_t around a scaling pass: A, the scaling and A^T run on the a1-line in
+// the registers of one thread (v3_stageA_scale_At).  sc: [E][NQ].
+// the inner three stages B^T, K, B (in place on x [b1][a2][a3]) are one out-of-line body shared
+// by both halves: loop A is sensitive to its instruction footprint
+template <int N1, int NC, int E, bool OOL>
+__device__ __noinline__ void apply_BtKB_t(const V3Tab T, double* __restrict__ x,
+                                          double* __restrict__ tmp) {
+  double* Z2 = tmp + E * NC * V3Dims<N1>::ZS;
+  vt3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, x, tmp);
+  __syncthreads();
+  vtv3_stageK<N1, NC, E>(threadIdx.x, 128, T, tmp, Z2);
+  __syncthreads();
+  v3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, Z2, x);
+  __syncthreads();
+}
+template <int N1, int NC, int E, bool OOL = false>
+__device__ __forceinline__ void apply_VtV_scaled_VtV_t(const VTab T, double* __restrict__ x,
+                                                       double* __restrict__ tmp,
+                                                       const double* __restrict__ sc) {
+  vt3_stageA<N1, E * NC>(threadIdx.x, 128, x);
+  __syncthreads();
+  apply_BtKB_t<N1, NC, E, OOL>(T.v3, x, tmp);
+  v3_stageA_scale_At<N1, E * NC, NC>(threadIdx.x, 128, x, sc);
+  __syncthreads();
+  apply_BtKB_t<N1, NC, E, OOL>(T.v3, x, tmp);
+  v3_stageA<N1, E * NC>(threadIdx.x, 128, x);
+  __syncthreads();
+}
+
 // dst [E][NC][N_f] = R src [E][NC][NQ]; all components per thread.  Rows of R on tensor-product
 // elements touch an arithmetic progression of volume nodes (one tensor line, or the N1 x N1
 // block behind a node of the collapsed face), so no column indices are loaded.
@@ -388,7 +419,8 @@ struct NodalCfg {
     return mx(mx(tmp(NC) + E * NC * Np, E * NC * Nf), DIM == 3 ? 2 * tmp(NC) : 0);
   }
   static __host__ __device__ constexpr size_t bytes(int NC, int Np, int Nf) {
-    return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf) + E * NC * rsep_per_column<N1>());
+    return sizeof(double) * (size_t)(E * NC * NQ + region(NC, Np, Nf) + E * NC * rsep_per_column<N1>() +
+                                     (DIM == 3 ? E * NQ : 0));
   }
 };
 
@@ -412,6 +444,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   double* bufP = tmp + Cf::tmp(NC);
   double* bufF = tmp;                      // aliases tmp/bufP; live only after the last apply
   double* rsc = tmp + Cf::region(NC, Np, Nf);   // scratch of the separable rows of R
+  double* scq = rsc + E * NC * rsep_per_column<N1>();   // W/J at the volume nodes (3-D only)
   const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
 
@@ -432,6 +465,9 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     jq = __ldcg(G.J_q + min(k0 + e, G.N_e - 1) * NQ + i);
   }
   SSE_LOOP(idx, E * NC * Np) bufP[idx] = (idx < Ev * NC * Np) ? __ldcg(u + k0 * NC * Np + idx) : 1.0;
+  if constexpr (DIM == 3) {   // W/J of the weight-adjusted mass inverse, read by line in the fused stage
+    if (proj == 2 && threadIdx.x < E * NQ) scq[threadIdx.x] = fdiv(__ldg(T.W + threadIdx.x % NQ), jq);
+  }
   __syncthreads();
   apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
@@ -459,15 +495,18 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
   if (proj == 2 && DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
     // projected entropy variables at the volume nodes, V M^-1 V^T (W J w) with
     // M^-1 = V^T (W/J) V:  two fused V V^T passes around the W/J scaling, no modal intermediate
+#ifdef SSE_NO_FUSED_SCALE   // A/B knob: two V V^T passes around a scaling pass
     if constexpr (DIM == 3) apply_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp);
     if (threadIdx.x < E * NQ) {
       const int i = threadIdx.x % NQ, e = threadIdx.x / NQ;
-      const double sc = fdiv(__ldg(T.W + i), jq);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] *= sc;
+      for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] *= scq[threadIdx.x];
     }
     __syncthreads();
     if constexpr (DIM == 3) apply_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp);
+#else
+    if constexpr (DIM == 3) apply_VtV_scaled_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp, scq);
+#endif
   } else if (proj == 2) {
     apply_Vt_t<DIM, N1, NC, E, true>(vtab(T), bufQ, bufP, tmp);
     // mass solve (weight-adjusted, M^-1 = I): V, W/J, V^T -- or the diagonal scaling
@@ -571,7 +610,16 @@ struct ProjectTetCfg {
   static constexpr int oX = 0;
   static constexpr int oZ = oX + COLS * NQ;
   static constexpr int oM = oX;   // the modal result overlays X, dead once the last B^T has run
-  static constexpr size_t bytes = sizeof(double) * (size_t)(oZ + G * VBLayout<N1, NCOL>::ZG);
+  // Systems (one element per column group): W/J at the nodes of the E elements is kept in shared
+  // memory and A, W/J, A^T run as one pass on the a1-line.  Scalar laws (every column another
+  // element) would double their footprint that way and keep the three passes.
+#ifdef SSE_NO_FUSED_SCALE
+  static constexpr bool FUSE_SCALE = false;
+#else
+  static constexpr bool FUSE_SCALE = (NCOL == NC);
+#endif
+  static constexpr int oS = oZ + G * VBLayout<N1, NCOL>::ZG;
+  static constexpr size_t bytes = sizeof(double) * (size_t)(oS + (FUSE_SCALE ? E * NQ : 0));
   static constexpr int NR = (E * NQ + 127) / 128;
 };
 
@@ -601,14 +649,20 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
     const long long k = min(k0 + e, Gm.N_e - 1);
     SSE_CP_ASYNC8(X + idx, r_q + k * NC * NQ + (idx - e * NC * NQ));
   }
-  double wij[NR];
+  double* SC = sm + Cf::oS;
+  double jq[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     const int idx = tid + r * 128;
-    wij[r] = 1.0;
+    jq[r] = 1.0;
+    if (idx < E * NQ) jq[r] = __ldcg(Gm.J_q + min(k0 + idx / NQ, Gm.N_e - 1) * NQ + idx % NQ);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int idx = tid + r * 128;
     if (idx < E * NQ) {
-      const int i = idx % NQ, e = idx / NQ;
-      wij[r] = fdiv(__ldg(T.W + i), __ldcg(Gm.J_q + min(k0 + e, Gm.N_e - 1) * NQ + i));
+      jq[r] = fdiv(__ldg(T.W + idx % NQ), jq[r]);
+      if constexpr (Cf::FUSE_SCALE) SC[idx] = jq[r];
     }
   }
   SSE_CP_ASYNC_WAIT_ALL();
@@ -621,21 +675,26 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
   __syncthreads();
   vb_stageB<N1, NCOL, G, false>(tid, 128, Z, X);
   __syncthreads();
-  vb_stageA<N1, NCOL, G, false>(tid, 128, X);
-  __syncthreads();
+  if constexpr (Cf::FUSE_SCALE) {
+    vb_stageA_scale_At<N1, NCOL, G, NC>(tid, 128, X, SC);   // A, W/J, A^T on the line in registers
+    __syncthreads();
+  } else {
+    vb_stageA<N1, NCOL, G, false>(tid, 128, X);
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int idx = tid + r * 128;
-    if (idx < E * NQ) {
-      const int i = idx % NQ, e = idx / NQ;
-      double* xb = X + e * NC * NQ + i;
+    for (int r = 0; r < NR; ++r) {
+      const int idx = tid + r * 128;
+      if (idx < E * NQ) {
+        const int i = idx % NQ, e = idx / NQ;
+        double* xb = X + e * NC * NQ + i;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) xb[c * NQ] *= wij[r];
+        for (int c = 0; c < NC; ++c) xb[c * NQ] *= jq[r];
+      }
     }
+    __syncthreads();
+    vb_stageA<N1, NCOL, G, true>(tid, 128, X);
+    __syncthreads();
   }
-  __syncthreads();
-  vb_stageA<N1, NCOL, G, true>(tid, 128, X);
-  __syncthreads();
   vb_stageB<N1, NCOL, G, true>(tid, 128, Z, X);
   __syncthreads();
   vb_stageC<N1, NCOL, G, true>(tid, 128, v3, M, Z);

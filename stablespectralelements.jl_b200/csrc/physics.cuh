@@ -77,6 +77,75 @@ __device__ __forceinline__ double frcp1(double x) {
   return fma(y, e, y);
 }
 
+// log / exp of the entropy-variable maps (loop A evaluates 475 logs and 225 exps per Tet p=4
+// element).  libdevice's versions carry their polynomial coefficients as 64-bit literals -- two
+// move instructions each on sm_100, half of the instructions of a call -- and branches for the
+// special cases.  These take the coefficients from constant memory and send anything that is not
+// a positive normal finite number (log) / not in |x| < 700 (exp) to libdevice out of line, so the
+// results for such arguments are libdevice's.
+//   flog: fdlibm's e_log.c scheme (x = 2^k m, m in [sqrt(1/2), sqrt(2)), s = f/(2+f), degree-7
+//         polynomial in s^2; < 1 ulp), the division through frcp;
+//   fexp: x = n ln2 + r, |r| <= ln2/2, exp(r) = 1 + r + r^2 q(r), q of degree 9 (Chebyshev
+//         interpolant, tools/fit_elementary.py: 0.66 ulp), 2^n added into the exponent field.
+__constant__ double c_el[24] = {
+    // [0..6] Lg1..Lg7, [7] pad
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+    2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+    1.479819860511658591e-01, 0.0,
+    // [8] ln2_hi, [9] ln2_lo, [10] log2(e), [11] 1.5 * 2^52 (round-to-nearest-integer shift)
+    6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634074, 6755399441055744.0,
+    // [12..21] q(r) of exp
+    5.00000000000000111e-01, 1.66666666666666685e-01, 4.16666666666241289e-02,
+    8.33333333333006153e-03, 1.38888889172137167e-03, 1.98412698630536177e-04,
+    2.48015212959543761e-05, 2.75572684599970641e-06, 2.76200884454097462e-07,
+    2.51003854955103203e-08, 0.0, 0.0};
+// one out-of-line copy each: loop A streams through ~34 KB of straight-line code per element and
+// is sensitive to its instruction footprint (profiles/r2_ab_log.md)
+#ifdef SSE_ELEM_INLINE
+#define SSE_ELEM_FN __device__ __forceinline__
+#else
+#define SSE_ELEM_FN static __device__ __noinline__
+#endif
+static __device__ __noinline__ double log_libdevice(double x) { return log(x); }
+static __device__ __noinline__ double exp_libdevice(double x) { return exp(x); }
+
+SSE_ELEM_FN double flog(double x) {
+#ifdef SSE_LIBDEVICE_ELEM   // A/B knob: libdevice's log / exp inline
+  return log(x);
+#endif
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_libdevice(x);
+  hi += 0x3ff00000 - 0x3fe6a09e;
+  const double dk = (double)((hi >> 20) - 0x3ff);
+  const double m = __hiloint2double((hi & 0x000fffff) + 0x3fe6a09e, lo);
+  const double f = m - 1.0;
+  const double s = f * frcp(2.0 + f);
+  const double z = s * s, w = z * z;
+  const double t1 = w * fma(w, fma(w, c_el[5], c_el[3]), c_el[1]);
+  const double t2 = fma(w, fma(w, fma(w, c_el[6], c_el[4]), c_el[2]), c_el[0]);
+  const double R = fma(z, t2, t1);
+  const double hfsq = 0.5 * f * f;
+  return fma(dk, c_el[8], -((hfsq - fma(s, hfsq + R, dk * c_el[9])) - f));
+}
+
+SSE_ELEM_FN double fexp(double x) {
+#ifdef SSE_LIBDEVICE_ELEM
+  return exp(x);
+#endif
+  if (!(fabs(x) < 700.0)) return exp_libdevice(x);
+  const double t = fma(x, c_el[10], c_el[11]);
+  const int n = __double2loint(t);
+  const double fn = t - c_el[11];
+  double r = fma(fn, -c_el[8], x);
+  r = fma(fn, -c_el[9], r);
+  double q = c_el[21];
+#pragma unroll
+  for (int i = 20; i >= 12; --i) q = fma(q, r, c_el[i]);
+  const double e = fma(r * r, q, r) + 1.0;
+  return __hiloint2double(__double2hiint(e) + (n << 20), __double2loint(e));
+}
+
 // logmean / inv_logmean (ConservationLaws.jl:132-156).  The reference's
 //   f^2 = (x(x-2y)+y^2)/(x(x+2y)+y^2) = ((x-y)/(x+y))^2,
 // and on its Taylor branch (f^2 < 1e-4), with z = f^2/3 + f^4/5 + f^6/7,
@@ -326,7 +395,7 @@ __device__ __forceinline__ void cons_to_entropy(const Phys& P, const double* u, 
     double p = gm1 * (u[DIM + 1] - k);
     double inv_p = frcp(p);
     // log(p / rho^gamma) = log p - gamma log rho (two logs instead of pow + log)
-    w[0] = (g - (log(p) - g * log(u[0]))) * P.inv_gm1 - k * inv_p;
+    w[0] = (g - (flog(p) - g * flog(u[0]))) * P.inv_gm1 - k * inv_p;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) w[1 + m] = u[1 + m] * inv_p;
     w[DIM + 1] = -u[0] * inv_p;
@@ -348,7 +417,7 @@ __device__ __forceinline__ void entropy_to_cons(const Phys& P, const double* w_i
     k = fdiv(k, 2.0 * w[DIM + 1]);
     double s = g - w[0] + k;
     // ((gm1 / (-w_last)^g)^(1/gm1)) exp(-s/gm1) = exp((log gm1 - g log(-w_last) - s) / gm1)
-    double rho_e = exp((P.log_gm1 - g * log(-w[DIM + 1]) - s) * inv_gm1);
+    double rho_e = fexp((P.log_gm1 - g * flog(-w[DIM + 1]) - s) * inv_gm1);
     u[0] = -w[DIM + 1] * rho_e;
 #pragma unroll
     for (int m = 0; m < DIM; ++m) u[1 + m] = w[1 + m] * rho_e;

@@ -1498,6 +1498,39 @@ int sse_measure_fp64_peak(int device, double* tflops) {
   return 0;
 }
 
+// The device log / exp of the entropy-variable maps (physics.cuh: flog, fexp) on host arrays:
+// test hook for their accuracy (tests/test_gpu_elementary.py; CPU: the emulation build).
+__global__ void k_probe_elementary(int which, const double* __restrict__ x, double* __restrict__ y,
+                                   long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = which == 0 ? flog(x[i]) : fexp(x[i]);
+}
+
+int sse_probe_elementary(int device, int which, const double* x, double* y, int64_t n) {
+  if (!x || !y || n < 0 || (which != 0 && which != 1)) return fail("bad argument");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(device));
+  double *dx = nullptr, *dy = nullptr;
+  CU(cudaMalloc(&dx, (size_t)n * sizeof(double)));
+  if (cudaMalloc(&dy, (size_t)n * sizeof(double)) != cudaSuccess) {
+    cudaFree(dx);
+    return fail("cudaMalloc failed");
+  }
+  cudaError_t e = cudaMemcpy(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int blocks = (int)std::min<int64_t>((n + 127) / 128, 4096);
+    k_probe_elementary SSE_LAUNCH(blocks, 128)(which, dx, dy, (long long)n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dy);
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  return 0;
+}
+
 // FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput with the same protocol: the evidence for
 // the "tensor cores only if DMMA beats the FP64 CUDA-core path" clause of the north star.  Eight
 // independent accumulator tiles per warp; FMA = 2 flops, 8*8*4 FMAs per instruction.

@@ -217,6 +217,39 @@ SSE_HD void vt3_stageA(int tid, int nthr, double* src) {
   }
 }
 
+// ---- stage A of V, a nodal scaling, stage A of V^T in one pass, in place on x
+// ([EC][b1][a2][a3] -> [EC][b1][a2][a3]): where V^T follows V with only a diagonal matrix between
+// them (the W/J of the weight-adjusted mass inverse between the two V V^T passes) the a1-line
+// stays in the registers of the thread that owns it -- one shared-memory round trip and two
+// barriers instead of three and four.  sc: [E][n^3] scaling at the volume nodes, NC columns per
+// element.
+template <int N1, int EC, int NC>
+SSE_HD void v3_stageA_scale_At(int tid, int nthr, double* x, const double* sc) {
+  using D = V3Dims<N1>;
+  for (int idx = tid; idx < EC * D::N2; idx += nthr) {
+    const int a23 = idx % D::N2, ec = idx / D::N2;
+    double* col = x + ec * D::N3 + a23;
+    const double* s = sc + (ec / NC) * D::N3 + a23;
+    double w[N1], y[N1];
+#pragma unroll
+    for (int b1 = 0; b1 < N1; ++b1) w[b1] = col[b1 * D::N2];
+#pragma unroll
+    for (int a1 = 0; a1 < N1; ++a1) {
+      double acc = 0.0;
+#pragma unroll
+      for (int b1 = 0; b1 < N1; ++b1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], w[b1], acc);
+      y[a1] = acc * s[a1 * D::N2];
+    }
+#pragma unroll
+    for (int b1 = 0; b1 < N1; ++b1) {
+      double acc = 0.0;
+#pragma unroll
+      for (int a1 = 0; a1 < N1; ++a1) acc = fma(c_wA[N1 - 3][a1 * N1 + b1], y[a1], acc);
+      col[b1 * D::N2] = acc;
+    }
+  }
+}
+
 // ---- V^T, stage B for one b1: W [EC][b1][a2][a3] -> Z [EC][pair][a3]
 template <int N1, int EC, int B1>
 SSE_HD void vt3_stageB_b1(int lane, const double* W, double* Z) {

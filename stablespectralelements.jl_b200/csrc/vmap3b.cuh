@@ -54,6 +54,41 @@ SSE_HD void vb_stageA(int tid, int nthr, double* X) {
   }
 }
 
+// ---- A, a nodal scaling, A^T in one pass on the a1-line (see v3_stageA_scale_At in vmap3.cuh).
+// sc: [elements of the CTA][n^3]; column c of group g belongs to element (g * NCOL + c) / NC.
+template <int N1, int NCOL, int G, int NC>
+SSE_HD void vb_stageA_scale_At(int tid, int nthr, double* X, const double* sc) {
+  using D = V3Dims<N1>;
+  for (int it = tid; it < G * D::N2; it += nthr) {
+    const int a23 = it % D::N2, g = it / D::N2;
+    double* col0 = X + g * NCOL * D::N3 + a23;
+    const double* s0 = sc + ((g * NCOL) / NC) * D::N3 + a23;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+      double* col = col0 + c * D::N3;
+      // NCOL % NC == 0 or NC % NCOL == 0 with whole elements per CTA: (g*NCOL + c)/NC - (g*NCOL)/NC == c/NC
+      const double* s = s0 + (c / NC) * D::N3;
+      double x[N1], y[N1];
+#pragma unroll
+      for (int q = 0; q < N1; ++q) x[q] = col[q * D::N2];
+#pragma unroll
+      for (int o = 0; o < N1; ++o) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N1; ++q) acc = fma(c_wA[N1 - 3][o * N1 + q], x[q], acc);
+        y[o] = acc * s[o * D::N2];
+      }
+#pragma unroll
+      for (int o = 0; o < N1; ++o) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N1; ++q) acc = fma(c_wA[N1 - 3][q * N1 + o], y[q], acc);
+        col[o * D::N2] = acc;
+      }
+    }
+  }
+}
+
 // ---- stage B: the b2-contraction, ragged in b1 (b2 < n - b1).  Group gi of b1 values:
 // gi = 0 -> {0};  gi > 0 -> {gi, n - gi} (one value when they coincide): n x n FMAs per column each
 // (n even: the middle group has n x n / 2).

@@ -78,7 +78,8 @@ EXPORTS = ["sse_last_error", "sse_version", "sse_create", "sse_destroy", "sse_re
            "sse_measure_dmma_peak", "sse_shard_range", "sse_shard_plan_build",
            "sse_nccl_unique_id", "sse_shard_create", "sse_shard_destroy", "sse_shard_handle",
            "sse_shard_get_plan", "sse_shard_residual", "sse_shard_rk_stage",
-           "sse_shard_rk_step_ck54", "sse_shard_time_residual", "sse_shard_sync"]
+           "sse_shard_rk_step_ck54", "sse_shard_time_residual", "sse_shard_sync",
+           "sse_probe_elementary"]
 
 
 SSE_MAX_PEERS = 64
@@ -137,6 +138,7 @@ def load_library(path: Optional[str] = None, allow_emulation: bool = False):
     lib.sse_device_bytes.restype = C.c_int64
     lib.sse_measure_fp64_peak.argtypes = [C.c_int, c_d_p]
     lib.sse_measure_dmma_peak.argtypes = [C.c_int, c_d_p]
+    lib.sse_probe_elementary.argtypes = [C.c_int, C.c_int, c_d_p, c_d_p, C.c_int64]
     lib.sse_time_derivative_range.argtypes = [vp, vp, C.c_int64, C.c_int64]
     lib.sse_set_stream.argtypes = [vp, vp]
     lib.sse_upload_state.argtypes = [vp, vp]
@@ -209,6 +211,18 @@ def shard_plan(mapP_cols: np.ndarray, N_e_global: int, rank: int, world: int):
     if rc != 0:
         raise RuntimeError("sse_shard_plan_build failed: " + lib.sse_last_error().decode())
     return plan, mp.reshape(n_loc, N_f).T, send[:plan.n_send].copy()
+
+
+def probe_elementary(which: str, x: np.ndarray, device: int = 0, lib=None) -> np.ndarray:
+    """The device ``log`` / ``exp`` of the entropy-variable maps applied to a host array."""
+    lib = lib or load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    rc = lib.sse_probe_elementary(device, {"log": 0, "exp": 1}[which], x.ctypes.data_as(c_d_p),
+                                  y.ctypes.data_as(c_d_p), x.size)
+    if rc != 0:
+        raise RuntimeError("sse_probe_elementary failed: " + lib.sse_last_error().decode())
+    return y
 
 
 def measure_dmma_peak(device: int = 0) -> float:

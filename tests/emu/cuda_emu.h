@@ -87,6 +87,14 @@ static inline typename std::common_type<A, B>::type max(A a, B b) {
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 // MUFU.RCP64H-like seed of the kernels' Newton reciprocals (rcp.approx.ftz.f64: ~2^-22)
 static inline double emu_rcp_approx(double x) { return (double)(float)(1.0 / x); }
+// bit-level views of a double (device intrinsics of the same names)
+static inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) {
+  long long b = ((long long)hi << 32) | (unsigned)lo;
+  double x; std::memcpy(&x, &b, 8); return x;
+}
+static inline double __int2double_rn(int v) { return (double)v; }
 
 // ------------------------------------------------------------------ launches
 namespace emu {

@@ -150,6 +150,12 @@ def test_one_element_tet_kernels_in_emulation(emu_lib, name, p, monkeypatch):
         d.close()
 
 
+def test_log_exp_of_the_entropy_maps_in_emulation(emu_lib):
+    """physics.cuh flog / fexp (same source, host build) against extended-precision NumPy."""
+    from test_gpu_elementary import check_elementary
+    check_elementary(lambda which, x: dev.probe_elementary(which, x, lib=emu_lib))
+
+
 def test_product_loader_refuses_emulation_build(emu_lib):
     import build_emu
     saved, dev._LIB = dev._LIB, None
