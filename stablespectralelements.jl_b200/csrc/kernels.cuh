@@ -68,6 +68,44 @@ enum { MASS_DIAGONAL = 0, MASS_WEIGHT_ADJUSTED = 1, MASS_CHOLESKY = 2 };
 
 #define SSE_LOOP(idx, total) for (int idx = threadIdx.x; idx < (total); idx += blockDim.x)
 
+// sum_i a[i] x[i], both in shared memory: four independent partial sums, unrolled by four
+// (k_physical with the operators staged in shared memory: a thread per output row)
+__device__ __forceinline__ double smem_dot(const double* __restrict__ a, const double* __restrict__ x,
+                                           int n) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    s0 = fma(a[i], x[i], s0);
+    s1 = fma(a[i + 1], x[i + 1], s1);
+    s2 = fma(a[i + 2], x[i + 2], s2);
+    s3 = fma(a[i + 3], x[i + 3], s3);
+  }
+  for (; i < n; ++i) s0 = fma(a[i], x[i], s0);
+  return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ double halfwarp_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// One output row of k_physical streamed from GLOBAL memory by a half-warp: NSEG row segments
+// a[s] (N_p x n row-major operators, n doubles each, contiguous) times vectors x[s] in shared
+// memory.  The 16 lanes read 16 consecutive doubles -- one full 128-byte line per segment step --
+// and the NSEG loads of a step are independent, so a lane keeps NSEG (x 2 rows, see the caller)
+// 8-byte loads in flight.  ok = false: a padding row (no loads, contributes 0).
+template <int NSEG>
+__device__ __forceinline__ double stream_row(const double* const* a, const double* const* x,
+                                             int n, int l16, bool ok, double acc) {
+  for (int i = l16; i < n; i += 16) {
+    double v[NSEG];
+#pragma unroll
+    for (int s_ = 0; s_ < NSEG; ++s_) v[s_] = ok ? __ldcs(a[s_] + i) : 0.0;
+#pragma unroll
+    for (int s_ = 0; s_ < NSEG; ++s_) acc = fma(v[s_], x[s_][i], acc);
+  }
+  return acc;
+}
+
 // ------------------------------------------------------------------ V and V^T
 // src: [E][NC][N_p] -> dst: [E][NC][N_q]; tmp holds 2*E*NC*n1^DIM doubles (warped only).
 template <int DIM>
@@ -736,24 +774,52 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   const long long k0 = G.k_begin + (long long)blockIdx.x * E;
   const int Ev = (int)min((long long)E, G.N_e - k0);
   // The per-element operators VOL[k][m] (N_p x N_q, d of them) and FAC[k] (N_p x N_f) are pure
-  // streaming data -- every entry is used once -- and 90 % of the kernel's bytes.  They are staged
-  // in shared memory with asynchronous copies issued FIRST, so that the whole operator block of
-  // the CTA's elements is in flight while the fluxes below are evaluated, and the row-times-vector
-  // products then read them from shared memory (a thread per output row reading its row from
-  // global memory touches 32 different cache lines per warp instruction: 35 % of the HBM peak).
+  // streaming data -- every entry is used once -- and 90 % of the kernel's bytes.
+  //  * default: they are never staged.  After the fluxes are in shared memory, a half-warp per
+  //    output row streams the row from global memory (stream_row): the CTA holds ~1 KB of shared
+  //    memory per element, ten CTAs are resident per SM, and the latency-bound phases of one CTA
+  //    (small gathers, flux evaluation, barriers) overlap the streaming phases of the others.
+  //  * staged (SSE_B200_PHYS_STAGED=1, the measured alternative): the blocks of the CTA's E
+  //    consecutive elements are contiguous in global memory, so ONE thread moves each with one
+  //    bulk asynchronous copy (cp.async.bulk, the TMA engine) issued first, completing on an
+  //    mbarrier every thread polls before the row-times-vector products read shared memory.
+  //    Bytes in flight are then bounded by shared memory held for a whole CTA lifetime
+  //    (~190 KB per SM / ~11 us = 37 % of the HBM peak, profiles/r2_ab_log.md).  A block whose
+  //    source, destination or size is not a multiple of 16 bytes falls back to cp.async.
+  const bool staged = (stage & 16) != 0;
+  stage &= 15;
   int nd = 1;
 #pragma unroll
   for (int m = 0; m < DIM; ++m) nd *= T.n1;
   const int nvol = DIM * Np * Nq, nfac = Np * Nf;
-  double* sOp = tmp + E * DIM * NC * (T.v_kind == V_WARPED ? 2 * nd : 0);   // [E][nvol + nfac]
-  for (int e = 0; e < E; ++e) {
-    const long long k = min(k0 + e, G.N_e - 1);
-    const double* vsrc = G.VOL + k * nvol;
-    const double* fsrc = G.FAC + k * nfac;
-    double* dst = sOp + e * (nvol + nfac);
-    for (int o = threadIdx.x; o < nvol; o += blockDim.x) SSE_CP_ASYNC8(dst + o, vsrc + o);
-    for (int o = threadIdx.x; o < nfac; o += blockDim.x) SSE_CP_ASYNC8(dst + nvol + o, fsrc + o);
+  double* sOp = tmp + E * DIM * NC * (T.v_kind == V_WARPED ? 2 * nd : 0);
+  sOp += ((size_t)sOp >> 3) & 1;            // 16-byte aligned: [E][nvol] | [E][nfac]
+  double* sVol = sOp;
+  double* sFac = sOp + (E * nvol + ((E * nvol) & 1));
+  __shared__ unsigned long long op_bar;
+  const long long nv = (long long)Ev * nvol, nfc = (long long)Ev * nfac;
+  const double* vsrc = G.VOL + k0 * nvol;
+  const double* fsrc = G.FAC + k0 * nfac;
+  const bool bulk_v = staged && (((size_t)vsrc & 15) == 0) && ((nv & 1) == 0) && SSE_SMEM_ALIGNED16(sVol);
+  const bool bulk_f = staged && (((size_t)fsrc & 15) == 0) && ((nfc & 1) == 0) && SSE_SMEM_ALIGNED16(sFac);
+  if (bulk_v || bulk_f) {
+    if (threadIdx.x == 0) {
+      SSE_MBAR_INIT(&op_bar, 1);
+      SSE_MBAR_INIT_FENCE();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      SSE_MBAR_EXPECT_TX(&op_bar, (bulk_v ? nv * 8 : 0) + (bulk_f ? nfc * 8 : 0));
+      if (bulk_v) SSE_BULK_G2S(sVol, vsrc, nv * 8, &op_bar);
+      if (bulk_f) SSE_BULK_G2S(sFac, fsrc, nfc * 8, &op_bar);
+    }
   }
+  if (staged && !bulk_v)
+    for (long long o = threadIdx.x; o < nv; o += blockDim.x) SSE_CP_ASYNC8(sVol + o, vsrc + o);
+  if (staged && !bulk_f)
+    for (long long o = threadIdx.x; o < nfc; o += blockDim.x) SSE_CP_ASYNC8(sFac + o, fsrc + o);
+  // half-warp roles of the streaming row products
+  const int hw = threadIdx.x >> 4, nhw = blockDim.x >> 4, l16 = threadIdx.x & 15;
 
   if (stage == 0) {
     // u_q as the "flux" in every direction; u* n at the facets (BR1: ½(u⁻+u⁺) n)
@@ -777,16 +843,40 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
     }
     SSE_CP_ASYNC_WAIT_ALL();
     __syncthreads();
-    SSE_LOOP(idx, E * DIM * NC * Np) {
-      int p = idx % Np, c = (idx / Np) % NC, m = (idx / (Np * NC)) % DIM, e = idx / (Np * NC * DIM);
-      const double* vol = sOp + e * (nvol + nfac) + (m * Np + p) * Nq;
-      const double* fac = sOp + e * (nvol + nfac) + nvol + p * Nf;
-      const double* uq = sFq + (e * NC + c) * Nq;
-      const double* un = sFn + ((e * DIM + m) * NC + c) * Nf;
-      double acc = 0.0;
-      for (int i = 0; i < Nq; ++i) acc = fma(vol[i], uq[i], acc);
-      for (int j = 0; j < Nf; ++j) acc = fma(fac[j], un[j], acc);
-      sP[idx] = -acc;
+    if (bulk_v || bulk_f) SSE_MBAR_WAIT(&op_bar, 0);
+    const int nrows = Ev * DIM * NC * Np;   // row idx = ((e * DIM + m) * NC + c) * Np + p
+    if (staged) {
+      SSE_LOOP(idx, nrows) {
+        int p = idx % Np, c = (idx / Np) % NC, m = (idx / (Np * NC)) % DIM, e = idx / (Np * NC * DIM);
+        sP[idx] = -(smem_dot(sVol + e * nvol + (m * Np + p) * Nq, sFq + (e * NC + c) * Nq, Nq) +
+                    smem_dot(sFac + e * nfac + p * Nf, sFn + ((e * DIM + m) * NC + c) * Nf, Nf));
+      }
+    } else {
+      // two rows per half-warp and step (block-uniform trip count: shuffles inside)
+      int p0 = hw % Np, g0 = hw / Np, p1 = (hw + nhw) % Np, g1 = (hw + nhw) / Np;   // g = idx / Np
+      for (int base = 0; base < nrows; base += 2 * nhw) {
+        double acc[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int pp = r ? p1 : p0, g = r ? g1 : g0;
+          const bool ok = base + r * nhw + hw < nrows;
+          const int c = g % NC, em = g / NC, m = em % DIM, e = ok ? em / DIM : 0;
+          const double* const av[1] = {G.VOL + ((k0 + e) * DIM + m) * (long long)Np * Nq + pp * Nq};
+          const double* const xv[1] = {sFq + (e * NC + c) * Nq};
+          const double* const af[1] = {G.FAC + (k0 + e) * (long long)nfac + pp * Nf};
+          const double* const xf[1] = {sFn + ((e * DIM + m) * NC + c) * Nf};
+          acc[r] = stream_row<1>(av, xv, Nq, l16, ok, 0.0);
+          acc[r] = stream_row<1>(af, xf, Nf, l16, ok, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double v = halfwarp_sum(acc[r]);
+          const int idx = base + r * nhw + hw;
+          if (idx < nrows && l16 == 0) sP[idx] = -v;
+        }
+        p0 += 2 * nhw; while (p0 >= Np) { p0 -= Np; ++g0; }
+        p1 += 2 * nhw; while (p1 >= Np) { p1 -= Np; ++g1; }
+      }
     }
     __syncthreads();
     apply_V<DIM>(T, E, DIM * NC, sP, sQ, tmp);
@@ -843,19 +933,47 @@ k_physical(Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
   }
   SSE_CP_ASYNC_WAIT_ALL();
   __syncthreads();
-  SSE_LOOP(idx, E * NC * Np) {
-    int p = idx % Np, c = (idx / Np) % NC, e = idx / (Np * NC);
-    double acc = 0.0;
+  if (bulk_v || bulk_f) SSE_MBAR_WAIT(&op_bar, 0);
+  const int nrows = Ev * NC * Np;   // row idx = (e * NC + c) * Np + p
+  if (staged) {
+    SSE_LOOP(idx, nrows) {
+      int p = idx % Np, c = (idx / Np) % NC, e = idx / (Np * NC);
+      double acc = smem_dot(sFac + e * nfac + p * Nf, sFn + (e * NC + c) * Nf, Nf);
 #pragma unroll
-    for (int m = 0; m < DIM; ++m) {
-      const double* vol = sOp + e * (nvol + nfac) + (m * Np + p) * Nq;
-      const double* f = sFq + ((e * DIM + m) * NC + c) * Nq;
-      for (int i = 0; i < Nq; ++i) acc = fma(vol[i], f[i], acc);
+      for (int m = 0; m < DIM; ++m)
+        acc += smem_dot(sVol + e * nvol + (m * Np + p) * Nq, sFq + ((e * DIM + m) * NC + c) * Nq, Nq);
+      sP[idx] = acc;
     }
-    const double* fac = sOp + e * (nvol + nfac) + nvol + p * Nf;
-    const double* fn = sFn + (e * NC + c) * Nf;
-    for (int j = 0; j < Nf; ++j) acc = fma(fac[j], fn[j], acc);
-    sP[idx] = acc;
+  } else {
+    int p0 = hw % Np, g0 = hw / Np, p1 = (hw + nhw) % Np, g1 = (hw + nhw) / Np;   // g = e * NC + c
+    for (int base = 0; base < nrows; base += 2 * nhw) {
+      double acc[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int pp = r ? p1 : p0, g = r ? g1 : g0;
+        const bool ok = base + r * nhw + hw < nrows;
+        const int c = g % NC, e = ok ? g / NC : 0;
+        const double* av[DIM];
+        const double* xv[DIM];
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) {
+          av[m] = G.VOL + ((k0 + e) * DIM + m) * (long long)Np * Nq + pp * Nq;
+          xv[m] = sFq + ((e * DIM + m) * NC + c) * Nq;
+        }
+        const double* const af[1] = {G.FAC + (k0 + e) * (long long)nfac + pp * Nf};
+        const double* const xf[1] = {sFn + (e * NC + c) * Nf};
+        acc[r] = stream_row<DIM>(av, xv, Nq, l16, ok, 0.0);
+        acc[r] = stream_row<1>(af, xf, Nf, l16, ok, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double v = halfwarp_sum(acc[r]);
+        const int idx = base + r * nhw + hw;
+        if (idx < nrows && l16 == 0) sP[idx] = v;
+      }
+      p0 += 2 * nhw; while (p0 >= Np) { p0 -= Np; ++g0; }
+      p1 += 2 * nhw; while (p1 >= Np) { p1 -= Np; ++g1; }
+    }
   }
   __syncthreads();
   store_result(T, G, rk, k0, E, NC, sP, dudt);

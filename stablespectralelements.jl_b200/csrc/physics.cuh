@@ -27,7 +27,53 @@
                    (unsigned)__cvta_generic_to_shared(dst)),                        \
                "l"(src) : "memory")
 #define SSE_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_all;" ::: "memory")
+// Bulk asynchronous copies (the TMA engine's 1-D copy, SASS UBLKCP) that complete on a
+// shared-memory mbarrier: one instruction moves a whole operator block; source, destination and
+// size are multiples of 16 bytes.
+#define SSE_SMEM_U32(p) ((unsigned)__cvta_generic_to_shared(p))
+#define SSE_MBAR_INIT(bar, n)                                                                 \
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), "r"(n) : "memory")
+#define SSE_MBAR_INIT_FENCE() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
+#define SSE_MBAR_EXPECT_TX(bar, bytes)                                                        \
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SSE_SMEM_U32(bar)), \
+               "r"((unsigned)(bytes)) : "memory")
+#define SSE_BULK_G2S(dst, src, bytes, bar)                                                    \
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
+               ::"r"(SSE_SMEM_U32(dst)), "l"(src), "r"((unsigned)(bytes)), "r"(SSE_SMEM_U32(bar)) : "memory")
+#define SSE_SMEM_ALIGNED16(p) ((SSE_SMEM_U32(p) & 15u) == 0u)
+// Every thread polls the phase.  A wait that outlives any plausible copy (2 s of wall clock on
+// %globaltimer, looked at every 4096 polls -- a bound in time, not in polls, so that preemption,
+// time slicing or a debugger cannot trip it) traps instead of hanging the device on a wrong byte
+// count.
+__device__ __forceinline__ void sse_mbar_wait(const void* bar, unsigned parity) {
+  const unsigned a = SSE_SMEM_U32(bar);
+  unsigned long long t0 = 0;
+  for (unsigned spin = 1;; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 4095u) == 0u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+#define SSE_MBAR_WAIT(bar, parity) sse_mbar_wait(bar, parity)
 #else
+// host emulation: the copy is done on the spot by the issuing fiber, the barrier ops are no-ops
+// (the kernels place a __syncthreads between the issue and the first use)
+#define SSE_MBAR_INIT(bar, n) ((void)(bar))
+#define SSE_MBAR_INIT_FENCE() ((void)0)
+#define SSE_MBAR_EXPECT_TX(bar, bytes) ((void)(bar))
+#define SSE_BULK_G2S(dst, src, bytes, bar) memcpy((void*)(dst), (const void*)(src), (size_t)(bytes))
+#define SSE_MBAR_WAIT(bar, parity) ((void)(bar))
+#define SSE_SMEM_ALIGNED16(p) ((((size_t)(p)) & 15u) == 0u)
 #define SSE_CP_ASYNC8(dst, src) (*(dst) = *(src))
 #define SSE_CP_ASYNC_WAIT_ALL() ((void)0)
 #define SSE_RCP_APPROX(y, x) y = emu_rcp_approx(x)

@@ -113,7 +113,8 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
     if (h->second_order && (h->b_stages & 1)) {
       RK none{};
       k_physical<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(
-          h->T, h->G, h->P, none, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 0, 1);
+          h->T, h->G, h->P, none, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b,
+          0 | (h->phys_staged ? 16 : 0), 1);
       h->launches++;
       if (!(h->b_stages & 2)) {
         CU(cudaGetLastError());
@@ -121,8 +122,8 @@ static int launch_b(sse_handle* h, double* dudt_dev, const RK& rk) {
       }
     }
     k_physical<DIM, LAW> SSE_LAUNCH(grid, h->thr_b, h->smem_b, h->stream)(
-        h->T, h->G, h->P, rk, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b, 1,
-        h->second_order);
+        h->T, h->G, h->P, rk, h->u_q, h->u_f, h->q_q, h->q_f, dudt_dev, h->E_b,
+        1 | (h->phys_staged ? 16 : 0), h->second_order);
   } else if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
     CU(cudaFuncSetAttribute(k_fluxdiff<DIM, LAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)h->smem_b));
@@ -267,6 +268,13 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   {
     const char* e = getenv("SSE_B200_PREFETCH");
     h->prefetch = (e && atoi(e) == 0) ? 0 : 1;
+    // k_physical: stage the per-element operators in shared memory with bulk copies, or stream
+    // their rows from global memory.  Measured on B200 (profiles/r2_ab_log.md): staging wins while
+    // an element's operators are small and N_q is not a multiple of 16 (a thread per staged row
+    // strides by N_q: 16-way bank conflicts for N_q = 16, 64); streaming wins otherwise.
+    const char* ps = getenv("SSE_B200_PHYS_STAGED");
+    const size_t op_bytes = sizeof(double) * ((size_t)cfg->d * cfg->N_p * cfg->N_q + (size_t)cfg->N_p * cfg->N_f);
+    h->phys_staged = ps ? (atoi(ps) == 1) : (cfg->N_q % 16 != 0 && op_bytes <= (size_t)48 * 1024);
   }
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -741,9 +749,9 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     return sizeof(double) * (size_t)E * ((size_t)Nc * Np + 2 * (size_t)Nc * Nq + (size_t)Nc * Nf + wtmp * Nc);
   };
   auto smem_b = [&](int E) -> size_t {
-    if (cfg->strategy == SSE_PHYSICAL_OPERATOR)   // + the staged operators VOL[k], FAC[k]
-      return sizeof(double) * (size_t)E * (d * Nc * ((size_t)2 * Nq + Nf + Np + wtmp) +
-                                           (size_t)d * Np * Nq + (size_t)Np * Nf);
+    if (cfg->strategy == SSE_PHYSICAL_OPERATOR)   // (+ the operators VOL[k], FAC[k] when staged)
+      return sizeof(double) * ((size_t)E * (d * Nc * ((size_t)2 * Nq + Nf + Np + wtmp) +
+                                            (h->phys_staged ? (size_t)d * Np * Nq + (size_t)Np * Nf : 0)) + 4);
     if (cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
       size_t sD = std::max((size_t)T.nnzRt * Nc, wtmp * Nc);
       return sizeof(double) * (size_t)E * ((size_t)NS * Nq + (size_t)d * d * Nq + (size_t)NS * Nf +
@@ -827,6 +835,17 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   if (h->fast_b ? pick(smem_b_fast, &h->E_b, &h->thr_b, &h->smem_b)
                 : pick(smem_b, &h->E_b, &h->thr_b, &h->smem_b))
     return -1;
+  if (cfg->strategy == SSE_PHYSICAL_OPERATOR) {
+    int e = h->E_b;
+    if (h->phys_staged) {
+      // operators staged with bulk copies: CTAs kept small (<= 40 KB: five or more per SM) and E
+      // even, which keeps every batch's blocks 16-byte aligned for odd N_p N_q / N_p N_f
+      while (e > 1 && (smem_b(e) > (size_t)40 * 1024 || (e & 1))) --e;
+    }
+    h->E_b = e;
+    h->smem_b = smem_b(e);
+    h->thr_b = std::max(128, std::min(256, ((e * Nq + 31) / 32) * 32));   // a half-warp per output row
+  }
   if (h->fast_b) h->E_b = std::max(1, 128 / Nq);     // FDCfg::EL
   if (h->fast_std) h->E_b = SSE_STD_NB;               // STCfg NB
   CU(cudaStreamSynchronize(h->stream));

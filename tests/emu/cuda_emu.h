@@ -229,6 +229,20 @@ static inline double __shfl_down_sync(unsigned, double v, int delta) {
   return r;
 }
 
+static inline double __shfl_xor_sync(unsigned, double v, int mask) {   // same contract as above
+  static std::vector<double> buf;
+  emu::State& s = emu::st();
+  const int nthr = (int)(s.bDim.x * s.bDim.y * s.bDim.z);
+  const int tid = s.current;
+  if ((int)buf.size() < nthr) buf.resize(nthr);
+  buf[tid] = v;
+  emu::barrier();
+  const int src = (tid & ~31) | ((tid & 31) ^ mask);
+  const double r = src < nthr ? buf[src] : v;
+  emu::barrier();
+  return r;
+}
+
 #define SSE_LAUNCH(...) * emu::Launcher(__VA_ARGS__)
 #define SSE_SHARED(name) double* name = emu::st().smem
 #define SSE_SHARED16(name) double* name = emu::st().smem
