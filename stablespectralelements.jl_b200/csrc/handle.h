@@ -62,7 +62,13 @@ struct sse_handle {
   // of chunk c (loop B of c may start once loop A of those chunks is enqueued)
   int n_chunk = 1;
   uint32_t chunk_need[SSE_MAX_CHUNKS] = {};
+  int64_t chunk_lo[SSE_MAX_CHUNKS + 1] = {};   // chunk c = elements [chunk_lo[c], chunk_lo[c+1])
   cudaEvent_t ev_chunk[SSE_MAX_CHUNKS] = {};
+  // host-buffer pipeline: loop A of the chunks runs on its own stream (ev_a[c] = loop A of chunk c
+  // done), so that its CTAs fill the tails of the loop-B kernels of earlier chunks
+  cudaStream_t a_stream = nullptr;
+  cudaEvent_t ev_a[SSE_MAX_CHUNKS] = {};
+  int host_a_stream = 1;
   unsigned next_ev = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> allocs;

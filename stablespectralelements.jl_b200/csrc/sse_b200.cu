@@ -227,7 +227,10 @@ int sse_destroy(sse_handle* h) {
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->a_stream) cudaStreamDestroy(h->a_stream);
   for (auto& e : h->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_a)
     if (e) cudaEventDestroy(e);
   delete h;
   return 0;
@@ -279,7 +282,13 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->a_stream, cudaStreamNonBlocking));
   for (auto& e : h->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : h->ev_a) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  {
+    const char* e = getenv("SSE_B200_HOST_ASTREAM");
+    h->host_a_stream = (e && atoi(e) == 0) ? 0 : 1;
+  }
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
 
   Tables& T = h->T;
@@ -679,13 +688,33 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     const int64_t ntr = (int64_t)Nf * (Ne + h->halo_elems);
     std::vector<int> toff((size_t)Nf * Ne), mp((size_t)Nf * Ne);
     h->n_chunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+    if (const char* ce = getenv("SSE_B200_HOST_CHUNKS"))
+      h->n_chunk = (int)std::min<int64_t>(std::min<int64_t>(SSE_MAX_CHUNKS, Ne), std::max(1, atoi(ce)));
     if (h->second_order || cfg->N_halo > 0) h->n_chunk = 1;
     const int nch = h->n_chunk;
-    auto chunk_of = [&](int64_t k) {   // inverse of lo(c) = Ne*c/nch
-      int c = (int)std::min<int64_t>(nch - 1, (k * nch) / Ne);
-      while (c + 1 < nch && (Ne * (c + 1)) / nch <= k) ++c;
-      while (c > 0 && (Ne * c) / nch > k) --c;
-      return c;
+    {
+      // Chunk boundaries of the host-buffer pipeline.  The first chunks are small so that the
+      // kernels start after a short upload, the last ones so that little is left to compute and
+      // to copy back once the last slice of u has landed: weights 1, 2, 4, 8, 8, ..., 8, 4, 2, 1
+      // (SSE_B200_HOST_TAPER=0: equal chunks).
+      const char* te = getenv("SSE_B200_HOST_TAPER");
+      const bool taper = !(te && atoi(te) == 0) && nch >= 8;
+      std::vector<double> w((size_t)nch, 8.0);
+      if (taper)
+        for (int i = 0; i < 3; ++i) w[i] = w[nch - 1 - i] = (double)(1 << i);
+      double tot = 0.0, run = 0.0;
+      for (double x : w) tot += x;
+      h->chunk_lo[0] = 0;
+      for (int c = 0; c < nch; ++c) {
+        run += w[c];
+        h->chunk_lo[c + 1] = std::max<int64_t>(h->chunk_lo[c] + 1, (int64_t)((double)Ne * (run / tot)));
+      }
+      h->chunk_lo[nch] = Ne;
+      for (int c = nch - 1; c > 0; --c)   // keep the boundaries strictly increasing
+        h->chunk_lo[c] = std::min(h->chunk_lo[c], h->chunk_lo[c + 1] - 1);
+    }
+    auto chunk_of = [&](int64_t k) {
+      return (int)(std::upper_bound(h->chunk_lo, h->chunk_lo + nch + 1, k) - h->chunk_lo) - 1;
     };
     for (int64_t g = 0; g < (int64_t)Nf * Ne; ++g) {
       int64_t t = mapP[g];
@@ -905,32 +934,61 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
   const int64_t Ne = h->cfg.N_e;
   const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
   const int nchunk = h->n_chunk;
-  auto lo = [&](int c) { return (Ne * c) / nchunk; };
+  auto lo = [&](int c) { return h->chunk_lo[c]; };
   // every exit path leaves the handle's element range whole again
   struct RangeGuard {
     sse_handle* h;
-    ~RangeGuard() { h->G.k_begin = 0; h->G.N_e = h->cfg.N_e; }
-  } guard{h};
+    cudaStream_t main;
+    ~RangeGuard() { h->G.k_begin = 0; h->G.N_e = h->cfg.N_e; h->stream = main; }
+  } guard{h, h->stream};
+  cudaStream_t const main_stream = h->stream;
+  cudaStream_t const a_stream = h->host_a_stream ? h->a_stream : main_stream;
   // the upload overwrites the resident state h->u: order it after whatever asynchronous work
   // (sse_rk_stage, sse_erk_step, sse_nodal_values, ...) is still queued on the main stream
   CU(cudaEventRecord(h->ev[3], h->stream));
   CU(cudaStreamWaitEvent(h->copy_stream, h->ev[3], 0));
+  // SSE_B200_HOST_TRACE=1: timeline of the pipeline on stderr (timing events per chunk)
+  static const bool trace = [] { const char* e = getenv("SSE_B200_HOST_TRACE"); return e && atoi(e) == 1; }();
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  // SSE_B200_HOST_NOCOPY=1 (diagnostic): the chunked kernel schedule without the copies
+  static const bool nocopy = [] { const char* e = getenv("SSE_B200_HOST_NOCOPY"); return e && atoi(e) == 1; }();
+  mark(h->copy_stream);                       // [0] start
   for (int c = 0; c < nchunk; ++c) {
+    if (!nocopy)
     CU(cudaMemcpyAsync(h->u + lo(c) * blk, u + lo(c) * blk, (lo(c + 1) - lo(c)) * blk * sizeof(double),
                        cudaMemcpyHostToDevice, h->copy_stream));
     CU(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
+    mark(h->copy_stream);                     // [1 + c] H2D of chunk c done
   }
+  std::vector<int> b_order;
   int rc = 0;
-  uint32_t a_done = 0, b_done = 0;
+  uint32_t a_done = 0, b_done = 0, a_seen = 0;   // a_seen: loop-A events the main stream waited for
   for (int c = 0; c < nchunk && !rc; ++c) {
-    CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
+    CU(cudaStreamWaitEvent(a_stream, h->ev_chunk[c], 0));
     h->G.k_begin = lo(c);
     h->G.N_e = lo(c + 1);
+    h->stream = a_stream;
     rc = run_a(h, h->u);
+    h->stream = main_stream;
+    if (a_stream != main_stream) CU(cudaEventRecord(h->ev_a[c], a_stream));
     a_done |= 1u << c;
     for (int b = 0; b < nchunk && !rc; ++b) {
       if ((b_done >> b) & 1u) continue;
-      if ((h->chunk_need[b] | (1u << b)) & ~a_done) continue;   // a neighbour chunk is missing
+      const uint32_t need = h->chunk_need[b] | (1u << b);
+      if (need & ~a_done) continue;   // a neighbour chunk is missing
+      if (a_stream != main_stream)
+        for (int n = 0; n < nchunk; ++n)
+          if ((need & ~a_seen) & (1u << n)) {
+            CU(cudaStreamWaitEvent(main_stream, h->ev_a[n], 0));
+            a_seen |= 1u << n;
+          }
       h->G.k_begin = lo(b);
       h->G.N_e = lo(b + 1);
       rc = run_b(h, h->dudt, rk);
@@ -939,9 +997,13 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
       // ev_chunk[b] was consumed by loop A of chunk b (b <= c), so it can be reused
       CU(cudaEventRecord(h->ev_chunk[b], h->stream));
       CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_chunk[b], 0));
+      mark(h->stream);                        // loop B of chunk b done
+      if (!nocopy)
       CU(cudaMemcpyAsync(dudt + lo(b) * blk, h->dudt + lo(b) * blk,
                          (lo(b + 1) - lo(b)) * blk * sizeof(double), cudaMemcpyDeviceToHost,
                          h->d2h_stream));
+      mark(h->d2h_stream);                    // D2H of chunk b done
+      b_order.push_back(b);
     }
   }
   h->G.k_begin = 0;
@@ -949,7 +1011,18 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
   if (rc) return -1;
   CU(cudaStreamSynchronize(h->copy_stream));
   CU(cudaStreamSynchronize(h->d2h_stream));
+  if (a_stream != main_stream) CU(cudaStreamSynchronize(a_stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (trace) {
+    auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[0], tev[i]); return ms; };
+    fprintf(stderr, "[sse host trace] %d chunks; H2D done at:", nchunk);
+    for (int c = 0; c < nchunk; ++c) fprintf(stderr, " %.2f", at(1 + c));
+    fprintf(stderr, "\n[sse host trace] chunk: loop B done / D2H done at:");
+    for (size_t i = 0; i < b_order.size(); ++i)
+      fprintf(stderr, " %d: %.2f / %.2f;", b_order[i], at(1 + nchunk + 2 * i), at(2 + nchunk + 2 * i));
+    fprintf(stderr, "\n");
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   return 0;
 }
 

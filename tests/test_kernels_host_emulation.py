@@ -150,6 +150,30 @@ def test_one_element_tet_kernels_in_emulation(emu_lib, name, p, monkeypatch):
         d.close()
 
 
+@pytest.mark.parametrize("chunks,taper", [(9, "1"), (9, "0"), (32, "1")])
+def test_host_buffer_pipeline_with_tapered_chunks(emu_lib, chunks, taper, monkeypatch):
+    """sse_residual(where=HOST) cut into element chunks of unequal size (small first and last
+    chunks, SSE_B200_HOST_TAPER) with the dependency-driven loop-B order: bitwise equal to the
+    device-resident residual of the same handle."""
+    monkeypatch.setenv("SSE_B200_HOST_TAPER", taper)
+    solver, u0 = CASES["euler2d_tri_p4_lf"][0]()
+    u = cases.rough_state(solver, u0, seed=3)
+    out = []
+    for n in (chunks, 1):
+        monkeypatch.setenv("SSE_B200_HOST_CHUNKS", str(n))
+        d = dev.DeviceResidual(solver)
+        try:
+            a = np.full_like(u, np.nan)
+            d.residual_host(u, a)
+            out.append(a)
+        finally:
+            d.close()
+    assert np.all(np.isfinite(out[0]))
+    assert np.array_equal(out[0], out[1])
+    ref = oc.semi_discrete_residual(oracle_problem(solver), u)
+    assert _rel(out[0], ref) < 1e-12
+
+
 def test_log_exp_of_the_entropy_maps_in_emulation(emu_lib):
     """physics.cuh flog / fexp (same source, host build) against extended-precision NumPy."""
     from test_gpu_elementary import check_elementary
