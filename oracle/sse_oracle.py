@@ -30,10 +30,18 @@ import numpy as np
 
 
 # =============================================================================== physics
+def _real(x):
+    """Floating-point view of x: FP64 unless the caller works in extended precision
+    (np.longdouble input runs the whole oracle in 80-bit arithmetic: the accuracy reference of
+    tests/test_oracle_extended_precision.py)."""
+    x = np.asarray(x)
+    return x if x.dtype == np.longdouble else np.asarray(x, dtype=np.float64)
+
+
 def logmean(x, y):
     """ConservationLaws/ConservationLaws.jl:132-145."""
-    x = np.asarray(x, dtype=np.float64)
-    y = np.asarray(y, dtype=np.float64)
+    x = _real(x)
+    y = _real(y)
     f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y)
     with np.errstate(divide="ignore", invalid="ignore"):
         taylor = (x + y) * 105 / (210 + f2 * (70 + f2 * (42 + f2 * 30)))
@@ -43,8 +51,8 @@ def logmean(x, y):
 
 def inv_logmean(x, y):
     """ConservationLaws/ConservationLaws.jl:147-156."""
-    x = np.asarray(x, dtype=np.float64)
-    y = np.asarray(y, dtype=np.float64)
+    x = _real(x)
+    y = _real(y)
     f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y)
     with np.errstate(divide="ignore", invalid="ignore"):
         taylor = (210 + f2 * (70 + f2 * (42 + f2 * 30))) / ((x + y) * 105)
@@ -73,7 +81,7 @@ def physical_flux(law, u, q=None):
         V = [u[..., m + 1] / rho for m in range(d)]
         p = gm1 * (u[..., -1] - 0.5 * sum(u[..., m + 1] * V[m] for m in range(d)))
         h_t = u[..., -1] + p
-        f = np.empty(u.shape + (d,))
+        f = np.empty(u.shape + (d,), dtype=u.dtype)
         for n in range(d):
             f[..., 0, n] = u[..., n + 1]
             for m in range(d):
@@ -112,7 +120,7 @@ def two_point_flux(law, flux_kind, uL, uR):
         C = 0.5 * sum(V_L[m] * V_R[m] for m in range(d)) + inv_gm1 * inv_logmean(
             uL[..., 0] / p_L, uR[..., 0] / p_R)
         shape = np.broadcast(uL[..., 0], uR[..., 0]).shape
-        f = np.empty(shape + (d + 2, d))
+        f = np.empty(shape + (d + 2, d), dtype=np.result_type(uL, uR))
         for n in range(d):
             f_rho = rho_avg * V_avg[n]
             f[..., 0, n] = f_rho

@@ -21,14 +21,16 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
 
-def _conditioning_floor(prob, u, ref):
-    """Relative change of the ORACLE's own residual under a +-1 ulp perturbation of its input.
-    For the low-Mach Taylor-Green state (p ~ 71, |V| ~ 1) this is ~2e-12: no two FP64
-    implementations (the Julia reference included) can agree below it, so the parity bound is
-    max(1e-12, 4 x this floor).  See DESIGN.md section 6."""
-    rng = np.random.default_rng(123)
-    up = u * (1.0 + rng.integers(-1, 2, size=u.shape) * 1.1e-16)
-    return _rel(oc.semi_discrete_residual(prob, up), ref)
+def _fp64_floor(prob, u, ref):
+    """Distance of the ORACLE's own FP64 residual from the same algorithm evaluated in 80-bit
+    extended precision (np.longdouble) on the same FP64 inputs, and that 80-bit residual.  For the
+    low-Mach Taylor-Green state (p ~ 71, |V| <= 1) round-off is amplified to ~5e-12 inside the
+    algorithm itself (the mathematical conditioning, a 1-ulp input perturbation evaluated in
+    80-bit arithmetic, is only 7e-14: tests/test_oracle_extended_precision.py), so no two FP64
+    implementations, the Julia reference included, can agree to 1e-12 on it.  See DESIGN.md
+    section 6."""
+    ref_x = oc.semi_discrete_residual(prob, u.astype(np.longdouble))
+    return _rel(ref.astype(np.longdouble), ref_x), ref_x
 
 
 def _check(solver, u, tol=TOL):
@@ -39,8 +41,11 @@ def _check(solver, u, tol=TOL):
     assert np.all(np.isfinite(dudt))
     err = _rel(dudt, ref)
     if err >= tol:
-        tol = max(tol, 4.0 * _conditioning_floor(prob, u, ref))
-    assert err < tol, (err, tol)
+        # the FP64 oracle is itself further than 1e-12 from the exact-arithmetic residual: the CUDA
+        # result must be as close to the 80-bit evaluation as the reference algorithm in FP64 is
+        floor, ref_x = _fp64_floor(prob, u, ref)
+        err_x = _rel(dudt.astype(np.longdouble), ref_x)
+        assert err_x < max(tol, 1.5 * floor), (err, err_x, floor)
     # the input must not be modified and a second call must reproduce the first
     d2 = np.empty_like(u)
     semi_discrete_residual(d2, u, solver, 0.0)
