@@ -424,12 +424,16 @@ struct NodalCfg {
   }
 };
 
+// Resident CTAs per SM the loop-A kernel is compiled for (register cap 65536 / (128 * MINB)).  The
+// kernel is latency-bound: Tet p=4 gains 2 % at 12 CTAs (40 registers, 8 bytes of spill) over 10
+// and loses 4 % at 16 (32 registers, 56 bytes); the other instantiations spill more at 40
+// registers and stay at 10 (profiles/r2_ab_log.md).
 #ifndef SSE_NODAL_MINB
-#define SSE_NODAL_MINB 10
+#define SSE_NODAL_MINB(DIM, N1) (((DIM) == 3 && (N1) == 5) ? 12 : 10)
 #endif
 
 template <int DIM, int N1, int LAW, bool COLLAPSED>
-__global__ void __launch_bounds__(128, SSE_NODAL_MINB)
+__global__ void __launch_bounds__(128, SSE_NODAL_MINB(DIM, N1))
 k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
                double* __restrict__ u_f, int proj) {
   constexpr int NC = LawTraits<DIM, LAW>::NC;

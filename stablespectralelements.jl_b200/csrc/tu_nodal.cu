@@ -31,7 +31,7 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
   CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
-  h->G.pf_dist = h->prefetch ? h->sm_count * SSE_NODAL_MINB * EL : 0;
+  h->G.pf_dist = h->prefetch ? h->sm_count * SSE_NODAL_MINB(DIM, N1) * EL : 0;
   k_nodal_tensor<DIM, N1, LAW, true> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
   h->launches++;
