@@ -445,6 +445,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    # host threads and pinned buffers of this rank on the GPU's own NUMA node (end-to-end path)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sse_b200.device import bind_host_to_gpu_numa_node
+    numa = bind_host_to_gpu_numa_node(local_rank) if os.environ.get("SSE_B200_NUMA_BIND", "1") != "0" else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -542,7 +546,8 @@ def main():
                     "l2": "inputs (geometry + state, > 6 GB per GPU) far exceed the 126 MB L2; "
                           "no flush needed",
                     "setup_s": main_r["setup_s"],
-                    "geometry": "device (sse_geometry_build)" if args.device_geometry else "host"},
+                    "geometry": "device (sse_geometry_build)" if args.device_geometry else "host",
+                    "numa_rank0": numa},
             "roofline": roofline, "kernel_ms": split, "clocks": main_r["clocks"],
             "gpu_launches": main_r["gpu_launches"], "e2e": main_r.get("e2e"),
         }

@@ -213,6 +213,42 @@ def shard_plan(mapP_cols: np.ndarray, N_e_global: int, rank: int, world: int):
     return plan, mp.reshape(n_loc, N_f).T, send[:plan.n_send].copy()
 
 
+def bind_host_to_gpu_numa_node(device: int = 0) -> dict:
+    """Best effort: restrict this process to the CPUs of the NUMA node the GPU hangs off, BEFORE
+    pinned host buffers are allocated (first touch then places them on that node), so that the
+    host<->device copies of ``sse_residual(where=HOST)`` do not cross the socket interconnect.
+    Returns what was found and done; never raises (containers often hide the topology)."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        sysdev = "/sys/bus/pci/devices/%s:%s" % (dom[-4:].lower(), rest.lower())
+        with open(sysdev + "/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        allowed = os.sched_getaffinity(0)
+        info["cpus_allowed"] = len(allowed)
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        local = allowed & cpus
+        info["cpus_on_node"] = len(local)
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            info["bound"] = True
+    except Exception as e:  # noqa: BLE001 -- topology files / NVML may be absent
+        info["error"] = type(e).__name__
+    return info
+
+
 def probe_elementary(which: str, x: np.ndarray, device: int = 0, lib=None) -> np.ndarray:
     """The device ``log`` / ``exp`` of the entropy-variable maps applied to a host array."""
     lib = lib or load_library()
