@@ -174,6 +174,23 @@ def test_host_buffer_pipeline_with_tapered_chunks(emu_lib, chunks, taper, monkey
     assert _rel(out[0], ref) < 1e-12
 
 
+@pytest.mark.parametrize("staged", ["0", "1"])
+def test_physical_operator_kernel_forms_in_emulation(emu_lib, staged, monkeypatch):
+    """Body of tests/test_gpu_variants.py::test_both_forms_of_the_physical_operator_kernel."""
+    import test_gpu_variants as tv
+    for case in ("advdiff2d_p3", "advdiff1d_p4", "adv2d_physical", "burgers2d_physical"):
+        tv.test_both_forms_of_the_physical_operator_kernel.__wrapped__(case, staged, monkeypatch) \
+            if hasattr(tv.test_both_forms_of_the_physical_operator_kernel, "__wrapped__") \
+            else tv.test_both_forms_of_the_physical_operator_kernel(case, staged, monkeypatch)
+
+
+def test_host_pipeline_knobs_in_emulation(emu_lib, monkeypatch):
+    """Body of tests/test_gpu_variants.py::test_host_buffer_pipeline_knobs_are_bitwise_neutral."""
+    import test_gpu_variants as tv
+    tv.test_host_buffer_pipeline_knobs_are_bitwise_neutral(
+        {"SSE_B200_HOST_CHUNKS": "9", "SSE_B200_HOST_ASTREAM": "0"}, monkeypatch)
+
+
 def test_log_exp_of_the_entropy_maps_in_emulation(emu_lib):
     """physics.cuh flog / fexp (same source, host build) against extended-precision NumPy."""
     from test_gpu_elementary import check_elementary
