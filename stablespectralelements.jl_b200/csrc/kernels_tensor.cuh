@@ -633,6 +633,11 @@ struct ProjectTetCfg {
 #ifndef SSE_PROJECT_TET_MINB
 #define SSE_PROJECT_TET_MINB 5
 #endif
+// two work items per column set in the ragged stages (all four warps busy, critical path of the
+// stage 3/5): measured 2.8 % SLOWER on loop B (the coefficient blocks are fetched twice) -- off
+#ifndef SSE_PROJECT_TET_SPLIT
+#define SSE_PROJECT_TET_SPLIT 1
+#endif
 
 template <int N1, int NC, int NCOL, int G>
 __global__ void __launch_bounds__(128, SSE_PROJECT_TET_MINB)
@@ -671,13 +676,15 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
   }
   SSE_CP_ASYNC_WAIT_ALL();
   __syncthreads();
+  // work items per column set in the ragged stages: two where both halves still fit one round
+  constexpr int SP = (SSE_PROJECT_TET_SPLIT == 2 && 2 * D::T2 * G <= 128) ? 2 : 1;
   vb_stageA<N1, NCOL, G, true>(tid, 128, X);
   __syncthreads();
-  vb_stageB<N1, NCOL, G, true>(tid, 128, Z, X);
+  vb_stageB<N1, NCOL, G, true, SP>(tid, 128, Z, X);
   __syncthreads();
-  vb_stageK<N1, NCOL, G>(tid, 128, v3, Z);
+  vb_stageK<N1, NCOL, G, SP>(tid, 128, v3, Z);
   __syncthreads();
-  vb_stageB<N1, NCOL, G, false>(tid, 128, Z, X);
+  vb_stageB<N1, NCOL, G, false, SP>(tid, 128, Z, X);
   __syncthreads();
   if constexpr (Cf::FUSE_SCALE) {
     vb_stageA_scale_At<N1, NCOL, G, NC>(tid, 128, X, SC);   // A, W/J, A^T on the line in registers
@@ -699,9 +706,9 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
     vb_stageA<N1, NCOL, G, true>(tid, 128, X);
     __syncthreads();
   }
-  vb_stageB<N1, NCOL, G, true>(tid, 128, Z, X);
+  vb_stageB<N1, NCOL, G, true, SP>(tid, 128, Z, X);
   __syncthreads();
-  vb_stageC<N1, NCOL, G, true>(tid, 128, v3, M, Z);
+  vb_stageC<N1, NCOL, G, true, SP>(tid, 128, v3, M, Z);
   __syncthreads();
   store_result(T, Gm, rk, k0, E, NC, M, dudt);
 }

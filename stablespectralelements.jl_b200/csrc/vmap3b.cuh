@@ -131,12 +131,12 @@ SSE_HD void vb_B_bwd(const double* xc, double* zc) {
 }
 // one out-of-line body per b1 group (inlined into the switch the compiler hoists the constant
 // loads of ALL groups in front of it)
-template <int N1, int NCOL, int GI, bool TRANSPOSE>
+template <int N1, int NCOL, int GI, bool TRANSPOSE, int C0 = 0, int C1 = NCOL>
 SSE_HD_NOINLINE void vb_stageB_group(double* zg, double* xg) {
   using D = V3Dims<N1>;
   constexpr int B2 = VBGroups<N1>::second(GI);
 #pragma unroll
-  for (int c = 0; c < NCOL; ++c) {
+  for (int c = C0; c < C1; ++c) {
     if constexpr (TRANSPOSE) {
       vb_B_bwd<N1, GI>(xg + c * D::N3, zg + c * D::ZS);
       if constexpr (B2 >= 0) vb_B_bwd<N1, B2>(xg + c * D::N3, zg + c * D::ZS);
@@ -146,30 +146,58 @@ SSE_HD_NOINLINE void vb_stageB_group(double* zg, double* xg) {
     }
   }
 }
+// SPLIT = 2: the columns of an item are shared by two work items (columns [0, H) and [H, NCOL),
+// H = ceil(NCOL / 2); the second halves are the upper half of the index range, so warps stay
+// uniform).  The ragged stages have G * 3 * n resp. G * T2 items -- 60 for four Tet p=4 elements,
+// two of a CTA's four warps -- and the kernels that use them wait at barriers more than anything
+// else (k_project_tet: 3.7 stalled warps per issue): halving the longest item shortens the
+// critical path of the stage although the coefficient block is fetched twice.
+template <int NCOL> struct VBSplit { static constexpr int H = (NCOL + 1) / 2; };
+
 // items (a3 fastest, then group-of-columns g, then b1 group gi): warps are (nearly) uniform in gi
-template <int N1, int NCOL, int G, bool TRANSPOSE>
+template <int N1, int NCOL, int G, bool TRANSPOSE, int SPLIT = 1>
 SSE_HD void vb_stageB(int tid, int nthr, double* Z, double* X) {
   using D = V3Dims<N1>;
-  constexpr int NG = VBGroups<N1>::NG;
-  for (int it = tid; it < NG * G * N1; it += nthr) {
+  constexpr int NG = VBGroups<N1>::NG, NI = NG * G * N1, H = VBSplit<NCOL>::H;
+  static_assert(SPLIT == 1 || SPLIT == 2, "one or two work items per column set");
+  for (int it0 = tid; it0 < SPLIT * NI; it0 += nthr) {
+    const int sub = it0 / NI, it = it0 - sub * NI;
     const int a3 = it % N1, g = (it / N1) % G, gi = it / (N1 * G);
     double* zg = Z + g * VBLayout<N1, NCOL>::ZG + a3;
     double* xg = X + g * NCOL * D::N3 + a3;
-    switch (gi) {
-      case 0: vb_stageB_group<N1, NCOL, 0, TRANSPOSE>(zg, xg); break;
-      case 1: vb_stageB_group<N1, NCOL, 1, TRANSPOSE>(zg, xg); break;
-      case 2: if constexpr (NG > 2) vb_stageB_group<N1, NCOL, 2, TRANSPOSE>(zg, xg); break;
-      default: break;
+    if (SPLIT == 1) {
+      switch (gi) {
+        case 0: vb_stageB_group<N1, NCOL, 0, TRANSPOSE>(zg, xg); break;
+        case 1: vb_stageB_group<N1, NCOL, 1, TRANSPOSE>(zg, xg); break;
+        case 2: if constexpr (NG > 2) vb_stageB_group<N1, NCOL, 2, TRANSPOSE>(zg, xg); break;
+        default: break;
+      }
+    } else if (sub == 0) {
+      switch (gi) {
+        case 0: vb_stageB_group<N1, NCOL, 0, TRANSPOSE, 0, H>(zg, xg); break;
+        case 1: vb_stageB_group<N1, NCOL, 1, TRANSPOSE, 0, H>(zg, xg); break;
+        case 2: if constexpr (NG > 2) vb_stageB_group<N1, NCOL, 2, TRANSPOSE, 0, H>(zg, xg); break;
+        default: break;
+      }
+    } else {
+      switch (gi) {
+        case 0: vb_stageB_group<N1, NCOL, 0, TRANSPOSE, H, NCOL>(zg, xg); break;
+        case 1: vb_stageB_group<N1, NCOL, 1, TRANSPOSE, H, NCOL>(zg, xg); break;
+        case 2: if constexpr (NG > 2) vb_stageB_group<N1, NCOL, 2, TRANSPOSE, H, NCOL>(zg, xg); break;
+        default: break;
+      }
     }
   }
 }
 
 // ---- pair stages: one item per (group, (b1,b2) pair), coefficients of the pair in registers
 // K: Z <- K[pair] Z in place (the two ragged b3-contractions of V V^T fused, vmap3.cuh)
-template <int N1, int NCOL, int G>
+template <int N1, int NCOL, int G, int SPLIT = 1>
 SSE_HD void vb_stageK(int tid, int nthr, V3Tab T, double* Z) {
   using D = V3Dims<N1>;
-  for (int it = tid; it < D::T2 * G; it += nthr) {
+  constexpr int NI = D::T2 * G, H = VBSplit<NCOL>::H;
+  for (int it0 = tid; it0 < SPLIT * NI; it0 += nthr) {
+    const int sub = it0 / NI, it = it0 - sub * NI;
     const int pr = it % D::T2, g = it / D::T2;
     double k[N1 * N1];
 #pragma unroll
@@ -177,6 +205,7 @@ SSE_HD void vb_stageK(int tid, int nthr, V3Tab T, double* Z) {
     double* zb = Z + g * VBLayout<N1, NCOL>::ZG + pr * N1;
 #pragma unroll
     for (int c = 0; c < NCOL; ++c) {
+      if (SPLIT == 2 && ((c < H) != (sub == 0))) continue;
       double z[N1];
 #pragma unroll
       for (int a = 0; a < N1; ++a) z[a] = zb[c * D::ZS + a];
@@ -191,10 +220,12 @@ SSE_HD void vb_stageK(int tid, int nthr, V3Tab T, double* Z) {
   }
 }
 // C (V): M [mode] -> Z [pair][a3];  C^T (V^T): Z -> M.  cnt = n - b1 - b2 modes per pair.
-template <int N1, int NCOL, int G, bool TRANSPOSE>
+template <int N1, int NCOL, int G, bool TRANSPOSE, int SPLIT = 1>
 SSE_HD void vb_stageC(int tid, int nthr, V3Tab T, double* M, double* Z) {
   using D = V3Dims<N1>;
-  for (int it = tid; it < D::T2 * G; it += nthr) {
+  constexpr int NI = D::T2 * G, H = VBSplit<NCOL>::H;
+  for (int it0 = tid; it0 < SPLIT * NI; it0 += nthr) {
+    const int sub = it0 / NI, it = it0 - sub * NI;
     const int pr = it % D::T2, g = it / D::T2;
     const int pt = SSE_LDG(T.pairtab + pr);
     const int b1 = pt & 15, b2 = (pt >> 4) & 15, s0 = pt >> 8;
@@ -209,6 +240,7 @@ SSE_HD void vb_stageC(int tid, int nthr, V3Tab T, double* M, double* Z) {
     double* zb = Z + g * VBLayout<N1, NCOL>::ZG + pr * N1;
 #pragma unroll
     for (int c = 0; c < NCOL; ++c) {
+      if (SPLIT == 2 && ((c < H) != (sub == 0))) continue;
       if constexpr (!TRANSPOSE) {
         double m[N1];
 #pragma unroll
