@@ -89,6 +89,7 @@ struct sse_handle {
   int erk_stages = 0;
   int sm_count = 0;             // SMs of cfg.device (grid / prefetch-distance sizing)
   int prefetch = 1;             // L2 prefetch one wave ahead in the specialised kernels
+  int proj_warp = 0;            // projection kernel: one element per warp (k_project_tet_w)
   int phys_staged = 0;          // k_physical: operators staged in shared memory by bulk copies (A/B)
   RK rk_override{};             // sse_shard_rk_stage: the RK epilogue of the range launches
   int use_rk_override = 0;

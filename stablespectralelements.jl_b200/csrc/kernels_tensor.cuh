@@ -713,6 +713,81 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
   store_result(T, Gm, rk, k0, E, NC, M, dudt);
 }
 
+// Warp-private edition of the projection for systems (NCOL = NC): every WARP owns one element --
+// its nodal block X, intermediate Z and W/J in its own slice of shared memory -- and runs the seven
+// stages on its own, separated by __syncwarp() only.  The work items of the batched engine carry 25
+// independent FMA chains each (all columns of a line / b1-group / pair), so a warp needs no other
+// warp to hide latency, and no warp ever waits at a block barrier for the two warps that hold the
+// 60 items of a ragged stage (k_project_tet: 3.7 stalled warps per issue at barriers).  The price
+// is lane utilisation (25 line items, 15 group / pair items per element on 32 lanes).
+#ifndef SSE_PROJECT_TET_W_EW
+#define SSE_PROJECT_TET_W_EW 1      // elements per warp
+#endif
+#ifndef SSE_PROJECT_TET_W_MINB
+#define SSE_PROJECT_TET_W_MINB 5
+#endif
+template <int N1, int NC>
+struct ProjectTetWarpCfg {
+  using D = V3Dims<N1>;
+  static constexpr int NQ = D::N3, WPB = 4, EW = SSE_PROJECT_TET_W_EW;   // warps per CTA, elements per warp
+  static constexpr int ZG = VBLayout<N1, NC>::ZG;
+  static constexpr int per_warp = ((EW * (NC * NQ + ZG + NQ)) + 1) & ~1;  // doubles, even
+  static constexpr size_t bytes = sizeof(double) * (size_t)(WPB * per_warp);
+};
+template <int N1, int NC>
+__global__ void __launch_bounds__(128, SSE_PROJECT_TET_W_MINB)
+k_project_tet_w(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* __restrict__ dudt) {
+  using Cf = ProjectTetWarpCfg<N1, NC>;
+  using D = V3Dims<N1>;
+  constexpr int NQ = Cf::NQ, EW = Cf::EW;
+  const Geo& Gm = G_;
+  SSE_SHARED16(sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* X = sm + warp * Cf::per_warp;          // [EW][NC][NQ]
+  double* Z = X + EW * NC * NQ;                  // [EW][ZG]
+  double* SC = Z + EW * Cf::ZG;                  // [EW][NQ]
+  double* M = X;                       // the modal result overlays X, dead once the last B^T has run
+  const long long k0 = Gm.k_begin + ((long long)blockIdx.x * Cf::WPB + warp) * EW;
+  const V3Tab v3{T.wC, T.wCt, T.pairtab, T.modetab, T.wK};
+  // (elements past the end compute on the last element and store nothing)
+  for (int idx = lane; idx < EW * NC * NQ; idx += 32) {
+    const int e = idx / (NC * NQ);
+    SSE_CP_ASYNC8(X + idx, r_q + min(k0 + e, Gm.N_e - 1) * NC * NQ + (idx - e * NC * NQ));
+  }
+  for (int i = lane; i < EW * NQ; i += 32)
+    SC[i] = fdiv(__ldg(T.W + i % NQ), __ldcg(Gm.J_q + min(k0 + i / NQ, Gm.N_e - 1) * NQ + i % NQ));
+  SSE_CP_ASYNC_WAIT_ALL();
+  __syncwarp();
+  vb_stageA<N1, NC, EW, true>(lane, 32, X);
+  __syncwarp();
+  vb_stageB<N1, NC, EW, true>(lane, 32, Z, X);
+  __syncwarp();
+  vb_stageK<N1, NC, EW>(lane, 32, v3, Z);
+  __syncwarp();
+  vb_stageB<N1, NC, EW, false>(lane, 32, Z, X);
+  __syncwarp();
+  vb_stageA_scale_At<N1, NC, EW, NC>(lane, 32, X, SC);
+  __syncwarp();
+  vb_stageB<N1, NC, EW, true>(lane, 32, Z, X);
+  __syncwarp();
+  vb_stageC<N1, NC, EW, true>(lane, 32, v3, M, Z);
+  __syncwarp();
+  const int blk = NC * T.N_p;
+  for (int idx = lane; idx < EW * blk; idx += 32) {
+    const long long k = k0 + idx / blk;
+    if (k < Gm.N_e) {
+      const long long g = k0 * blk + idx;
+      if (rk.mode == 0) {
+        dudt[g] = M[idx];
+      } else {
+        const double kk = rk.a * rk.k[g] + rk.dt * M[idx];
+        rk.k[g] = kk;
+        rk.u[g] += rk.b * kk;
+      }
+    }
+  }
+}
+
 // ==================================================== loop B, flux-differencing form
 // Compile-time geometry of the specialised loop-B kernel: EL elements per 128-thread CTA,
 // NF facet nodes, and the shared-memory carve-up (in doubles; regions holding double2 start

@@ -275,6 +275,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     // their rows from global memory.  Measured on B200 (profiles/r2_ab_log.md): staging wins while
     // an element's operators are small and N_q is not a multiple of 16 (a thread per staged row
     // strides by N_q: 16-way bank conflicts for N_q = 16, 64); streaming wins otherwise.
+    if (const char* pw = getenv("SSE_B200_PROJ_WARP")) h->proj_warp = atoi(pw);
     const char* ps = getenv("SSE_B200_PHYS_STAGED");
     const size_t op_bytes = sizeof(double) * ((size_t)cfg->dim * cfg->N_p * cfg->N_q + (size_t)cfg->N_p * cfg->N_f);
     h->phys_staged = ps ? (atoi(ps) == 1) : (cfg->N_q % 16 != 0 && op_bytes <= (size_t)48 * 1024);

@@ -28,8 +28,17 @@ static int launch_b_fast(sse_handle* h, double* dudt_dev, const RK& rk) {
       k_fluxdiff_nodal<DIM, N1, LAW, COLLAPSED, KC> SSE_LAUNCH(grid, 128, smem, h->stream)(
           h->F, h->T, h->G, h->P, h->u_q, h->u_f, h->r_q);
       const int pgrid = (int)((h->G.N_e - h->G.k_begin + EP - 1) / EP);
-      k_project_tet<N1, Cf::NC, Cf::NC, EP> SSE_LAUNCH(pgrid, 128, Pf::bytes, h->stream)(
-          h->T, h->G, rk, h->r_q, dudt_dev);
+      if (h->proj_warp) {   // one element per warp, no block barriers
+        using Wf = ProjectTetWarpCfg<N1, Cf::NC>;
+        CU(cudaFuncSetAttribute(k_project_tet_w<N1, Cf::NC>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Wf::bytes));
+        const int wgrid = (int)((h->G.N_e - h->G.k_begin + Wf::WPB * Wf::EW - 1) / (Wf::WPB * Wf::EW));
+        k_project_tet_w<N1, Cf::NC> SSE_LAUNCH(wgrid, 128, Wf::bytes, h->stream)(
+            h->T, h->G, rk, h->r_q, dudt_dev);
+      } else {
+        k_project_tet<N1, Cf::NC, Cf::NC, EP> SSE_LAUNCH(pgrid, 128, Pf::bytes, h->stream)(
+            h->T, h->G, rk, h->r_q, dudt_dev);
+      }
       h->launches += 2;
       CU(cudaGetLastError());
       return 0;

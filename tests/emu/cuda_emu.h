@@ -69,6 +69,9 @@ inline void barrier() {   // __syncthreads(): back to the scheduler, resumed aft
 }  // namespace emu
 
 static inline void __syncthreads() { emu::barrier(); }
+// __syncwarp(): valid in the emulation where every warp of the block executes the same number of
+// them (the warp-private kernels do): a block-wide barrier is then a (stricter) substitute
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }

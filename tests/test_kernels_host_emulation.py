@@ -191,6 +191,29 @@ def test_host_pipeline_knobs_in_emulation(emu_lib, monkeypatch):
         {"SSE_B200_HOST_CHUNKS": "9", "SSE_B200_HOST_ASTREAM": "0"}, monkeypatch)
 
 
+@pytest.mark.parametrize("name", ["euler3d_tet_p4_warp_lf", "euler3d_tet_p3_warp_ec"])
+def test_warp_private_projection_in_emulation(emu_lib, name, monkeypatch):
+    """k_project_tet_w (one element per warp, __syncwarp between the stages) is bitwise equal to
+    the CTA-level batched projection kernel: same work items, same arithmetic per item."""
+    solver, u0 = CASES[name][0]()
+    u = cases.rough_state(solver, u0, seed=6)
+    out = []
+    for pw in ("0", "1"):
+        monkeypatch.setenv("SSE_B200_PROJ_WARP", pw)
+        d = dev.DeviceResidual(solver)
+        try:
+            emu_lib.emu_launch_log()
+            a = np.full_like(u, np.nan)
+            d.residual_host(u, a)
+            launched = emu_lib.emu_launch_log().decode()
+            out.append(a)
+        finally:
+            d.close()
+    assert "k_project_tet_w" in launched
+    assert np.all(np.isfinite(out[1]))
+    assert np.array_equal(out[0], out[1])
+
+
 def test_log_exp_of_the_entropy_maps_in_emulation(emu_lib):
     """physics.cuh flog / fexp (same source, host build) against extended-precision NumPy."""
     from test_gpu_elementary import check_elementary
