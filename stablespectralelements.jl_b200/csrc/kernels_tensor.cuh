@@ -635,6 +635,9 @@ struct ProjectTetCfg {
 #endif
 // two work items per column set in the ragged stages (all four warps busy, critical path of the
 // stage 3/5): measured 2.8 % SLOWER on loop B (the coefficient blocks are fetched twice) -- off
+#ifndef SSE_PROJECT_TET_REGSCALE
+#define SSE_PROJECT_TET_REGSCALE 1   // scalar laws: A (W/J) A^T fused with the scaling in registers
+#endif
 #ifndef SSE_PROJECT_TET_SPLIT
 #define SSE_PROJECT_TET_SPLIT 1
 #endif
@@ -659,19 +662,38 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
     SSE_CP_ASYNC8(X + idx, r_q + k * NC * NQ + (idx - e * NC * NQ));
   }
   double* SC = sm + Cf::oS;
-  double jq[NR];
+  // W/J.  Systems: in shared memory, read by line in the fused stage.  Scalar laws with one line
+  // item per thread (REG_SCALE): the 5 x NCOL values of the thread's own line in registers.
+  // Otherwise: the thread's NR nodes in registers for a separate scaling pass.
+  constexpr bool REG_SCALE = !Cf::FUSE_SCALE && NC == 1 && G * D::N2 <= 128 && SSE_PROJECT_TET_REGSCALE;
+  constexpr int NJ = REG_SCALE ? NCOL * N1 : NR;
+  double jq[NJ];
+  if constexpr (REG_SCALE) {
+    const int a23 = tid % D::N2, g = min(tid / D::N2, G - 1);
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int idx = tid + r * 128;
-    jq[r] = 1.0;
-    if (idx < E * NQ) jq[r] = __ldcg(Gm.J_q + min(k0 + idx / NQ, Gm.N_e - 1) * NQ + idx % NQ);
-  }
+    for (int c = 0; c < NCOL; ++c)
 #pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    const int idx = tid + r * 128;
-    if (idx < E * NQ) {
-      jq[r] = fdiv(__ldg(T.W + idx % NQ), jq[r]);
-      if constexpr (Cf::FUSE_SCALE) SC[idx] = jq[r];
+      for (int a1 = 0; a1 < N1; ++a1)
+        jq[c * N1 + a1] = __ldcg(Gm.J_q + min(k0 + g * NCOL + c, Gm.N_e - 1) * NQ + a1 * D::N2 + a23);
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+      for (int a1 = 0; a1 < N1; ++a1)
+        jq[c * N1 + a1] = fdiv(__ldg(T.W + a1 * D::N2 + a23), jq[c * N1 + a1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int idx = tid + r * 128;
+      jq[r] = 1.0;
+      if (idx < E * NQ) jq[r] = __ldcg(Gm.J_q + min(k0 + idx / NQ, Gm.N_e - 1) * NQ + idx % NQ);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int idx = tid + r * 128;
+      if (idx < E * NQ) {
+        jq[r] = fdiv(__ldg(T.W + idx % NQ), jq[r]);
+        if constexpr (Cf::FUSE_SCALE) SC[idx] = jq[r];
+      }
     }
   }
   SSE_CP_ASYNC_WAIT_ALL();
@@ -688,6 +710,9 @@ k_project_tet(Tables T, Geo G_, RK rk, const double* __restrict__ r_q, double* _
   __syncthreads();
   if constexpr (Cf::FUSE_SCALE) {
     vb_stageA_scale_At<N1, NCOL, G, NC>(tid, 128, X, SC);   // A, W/J, A^T on the line in registers
+    __syncthreads();
+  } else if constexpr (REG_SCALE) {
+    vb_stageA_scale_At_regs<N1, NCOL, G>(tid, X, jq);
     __syncthreads();
   } else {
     vb_stageA<N1, NCOL, G, false>(tid, 128, X);

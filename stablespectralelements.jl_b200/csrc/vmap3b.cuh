@@ -89,6 +89,39 @@ SSE_HD void vb_stageA_scale_At(int tid, int nthr, double* X, const double* sc) {
   }
 }
 
+// The same pass with the scaling of the item's own line in REGISTERS (scalar laws: every column is
+// another element, so each W/J value is used exactly once; one item per thread, G * n^2 <= nthr).
+// sc[c * N1 + a1]: scaling of column c at the a1-th node of the thread's line.
+template <int N1, int NCOL, int G>
+SSE_HD void vb_stageA_scale_At_regs(int tid, double* X, const double (&sc)[NCOL * N1]) {
+  using D = V3Dims<N1>;
+  if (tid < G * D::N2) {
+    const int a23 = tid % D::N2, g = tid / D::N2;
+    double* col0 = X + g * NCOL * D::N3 + a23;
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+      double* col = col0 + c * D::N3;
+      double x[N1], y[N1];
+#pragma unroll
+      for (int q = 0; q < N1; ++q) x[q] = col[q * D::N2];
+#pragma unroll
+      for (int o = 0; o < N1; ++o) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N1; ++q) acc = fma(c_wA[N1 - 3][o * N1 + q], x[q], acc);
+        y[o] = acc * sc[c * N1 + o];
+      }
+#pragma unroll
+      for (int o = 0; o < N1; ++o) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N1; ++q) acc = fma(c_wA[N1 - 3][q * N1 + o], y[q], acc);
+        col[o * D::N2] = acc;
+      }
+    }
+  }
+}
+
 // ---- stage B: the b2-contraction, ragged in b1 (b2 < n - b1).  Group gi of b1 values:
 // gi = 0 -> {0};  gi > 0 -> {gi, n - gi} (one value when they coincide): n x n FMAs per column each
 // (n even: the middle group has n x n / 2).
