@@ -571,8 +571,15 @@ struct NodalBatchCfg {
   }
 };
 
+#ifndef SSE_NODALB_MINB
+#define SSE_NODALB_MINB 0
+#endif
 template <int DIM, int N1, int LAW, bool COLLAPSED, int NB>
+#if SSE_NODALB_MINB > 0
+__global__ void __launch_bounds__(128, SSE_NODALB_MINB)
+#else
 __global__ void __launch_bounds__(128)
+#endif
 k_nodal_batched(Tables T, Geo G, const double* __restrict__ u, double* __restrict__ u_q,
                 double* __restrict__ u_f) {
   static_assert(LawTraits<DIM, LAW>::NC == 1, "scalar conservation laws only");
@@ -1303,8 +1310,11 @@ struct STCfg {
 // PROJ = true: the projection / mass solve runs as the tail of this kernel; PROJ = false: the
 // nodal residual goes to global memory (dudt = r_q here) and k_project_tet finishes it, 25 elements
 // per CTA on the batched engine.
+#ifndef SSE_STD_MINB
+#define SSE_STD_MINB 12    // resident CTAs per SM the config-3 operator kernel is compiled for (40 registers; 10: +2.6 %, 16: spills, +60 %)
+#endif
 template <int DIM, int N1, int LAW, int KC, int NB, bool PROJ>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PROJ ? 9 : SSE_STD_MINB)   // (the fused-projection form spills at 40 registers)
 k_standard_tensor(FastTables F, Tables T, Geo G, Phys P, RK rk, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt) {
   static_assert(LAW != LAW_EULER, "scalar conservation laws only");

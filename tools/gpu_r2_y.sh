@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, session Y: config 3 with the fused A (W/J) A^T stage of the scalar projection (scaling in registers)
 mkdir -p gpurun_out
-for lib in stablespectralelements.jl_b200/libsse_b200.so build/variants/noreg.so stablespectralelements.jl_b200/libsse_b200.so; do
+for lib in stablespectralelements.jl_b200/libsse_b200.so build/variants/*.so stablespectralelements.jl_b200/libsse_b200.so; do
   echo "== $(basename $lib .so)"
   SSE_B200_LIB=$PWD/$lib CFG3_M=32 timeout 200 python tools/bench_configs.py 3 2>/dev/null | python -c "
 import json,sys
