@@ -152,3 +152,23 @@ def test_host_buffer_pipeline_knobs_are_bitwise_neutral(env, monkeypatch):
             d.close()
     assert np.all(np.isfinite(outs[0]))
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_warp_private_projection_matches_the_batched_kernel(monkeypatch):
+    """SSE_B200_PROJ_WARP=1: k_project_tet_w (one element per warp, __syncwarp between the stages)
+    against the CTA-level k_project_tet: the same work items with the same arithmetic."""
+    from sse_b200 import device as dev
+    solver, u0 = cases.euler_tet_case(p=4, M=4, lazy=True, warp=True, ic="periodic")
+    u = cases.rough_state(solver, u0, seed=7)
+    outs = []
+    for pw in ("0", "1"):
+        monkeypatch.setenv("SSE_B200_PROJ_WARP", pw)
+        d = dev.DeviceResidual(solver)
+        try:
+            dudt = np.full_like(u, np.nan)
+            d.residual_host(u, dudt)
+            outs.append(dudt)
+        finally:
+            d.close()
+    assert np.all(np.isfinite(outs[1]))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[0]))
