@@ -37,7 +37,8 @@ int sse_fail(const char* fmt, ...);
                   cudaGetErrorString(e_));                                            \
   } while (0)
 
-#define SSE_MAX_CHUNKS 32
+#define SSE_MAX_CHUNKS 64       // bit masks of chunks are 64 bits wide
+#define SSE_DEFAULT_CHUNKS 32   // host-buffer pipeline (SSE_B200_HOST_CHUNKS overrides, <= SSE_MAX_CHUNKS)
 
 // Tuning knobs of the scalar standard-form kernels (elements per CTA riding along as components);
 // the defaults are the measured optimum, tools/gpu_variants.sh sweeps -D overrides.
@@ -61,7 +62,7 @@ struct sse_handle {
   // host-buffer pipeline: chunk_need[c] = bit mask of the element chunks that hold a neighbour
   // of chunk c (loop B of c may start once loop A of those chunks is enqueued)
   int n_chunk = 1;
-  uint32_t chunk_need[SSE_MAX_CHUNKS] = {};
+  uint64_t chunk_need[SSE_MAX_CHUNKS] = {};
   int64_t chunk_lo[SSE_MAX_CHUNKS + 1] = {};   // chunk c = elements [chunk_lo[c], chunk_lo[c+1])
   cudaEvent_t ev_chunk[SSE_MAX_CHUNKS] = {};
   // host-buffer pipeline: loop A of the chunks runs on its own stream (ev_a[c] = loop A of chunk c
@@ -90,6 +91,8 @@ struct sse_handle {
   int sm_count = 0;             // SMs of cfg.device (grid / prefetch-distance sizing)
   int prefetch = 1;             // L2 prefetch one wave ahead in the specialised kernels
   int proj_warp = 0;            // projection kernel: one element per warp (k_project_tet_w)
+  int r_sep_only = 0;           // rows of R: tensor lines and separable collapsed-face blocks only
+  int nodal_rt_proj = 0;        // loop A: keep the run-time projection mode (SSE_B200_NODAL_RT_PROJ=1)
   int phys_staged = 0;          // k_physical: operators staged in shared memory by bulk copies (A/B)
   RK rk_override{};             // sse_shard_rk_stage: the RK epilogue of the range launches
   int use_rk_override = 0;

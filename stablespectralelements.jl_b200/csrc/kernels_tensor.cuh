@@ -275,14 +275,16 @@ __device__ __forceinline__ void apply_VtV_scaled_VtV_t(const VTab T, double* __r
 // scratch doubles apply_R_t needs per column for the separable collapsed-face rows
 template <int N1> __host__ __device__ constexpr int rsep_per_column() { return N1 * N1; }
 
-template <int NQ, int NC, int E, int Nf, int N1>
+// SEP_ONLY: every row of R is either a tensor line (N1 terms) or a separable collapsed-face row
+// (T.R_ng > 0, checked by the launcher): the dense-row forms are not compiled
+template <int NQ, int NC, int E, int Nf, int N1, bool SEP_ONLY = false>
 __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restrict__ src,
                                           double* __restrict__ dst, double* __restrict__ tsc) {
   // Collapsed face: R[(f1,f2)][a1=f1][a2][a3] = E[f2][a2] r3[a3] (Kronecker factors of
   // tensor_simplex.jl:221-306), so the a3-contraction is shared by the N1 rows of a group:
   // 2 * N1 instead of N1^2 terms per row, and every row of R costs the same.
   const int ng = T.R_ng;
-  if (ng > 0) {
+  if (SEP_ONLY || ng > 0) {
     SSE_LOOP(idx, E * NC * ng * N1) {
       const int a2 = idx % N1, g = (idx / N1) % ng, ec = idx / (N1 * ng);
       const double* s0 = src + ec * NQ + __ldg(T.R_gstart + g) + a2 * N1;
@@ -309,7 +311,7 @@ __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restr
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[c] = fma(v, s0[c * NQ + q * stride], acc[c]);
       }
-    } else if (ng > 0 && cnt == N1 * N1 && stride == 1) {
+    } else if (SEP_ONLY || (ng > 0 && cnt == N1 * N1 && stride == 1)) {
       const double* t0 = tsc + (e * NC * ng + __ldg(T.R_grp + j)) * N1;
 #pragma unroll
       for (int a2 = 0; a2 < N1; ++a2) {
@@ -432,10 +434,15 @@ struct NodalCfg {
 #define SSE_NODAL_MINB(DIM, N1) (((DIM) == 3 && (N1) == 5) ? 12 : 10)
 #endif
 
-template <int DIM, int N1, int LAW, bool COLLAPSED>
+// PROJ_CT: -1 = the projection mode is the run-time argument; 2 = compiled for the entropy
+// projection only (3-D: warped-product V with the weight-adjusted mass solver, checked by the
+// launcher) -- the other modes' code and their tests leave the kernel (Tet p=4 Euler: 4096 -> 3496
+// SASS instructions, loop A -5.2 % on B200, profiles/r2_ab_log.md session AA)
+template <int DIM, int N1, int LAW, bool COLLAPSED, int PROJ_CT = -1>
 __global__ void __launch_bounds__(128, SSE_NODAL_MINB(DIM, N1))
 k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __restrict__ u_q,
-               double* __restrict__ u_f, int proj) {
+               double* __restrict__ u_f, int proj_rt) {
+  const int proj = PROJ_CT >= 0 ? PROJ_CT : proj_rt;
   constexpr int NC = LawTraits<DIM, LAW>::NC;
   constexpr int NQ = ipow(N1, DIM);
   using Cf = NodalCfg<DIM, N1>;
@@ -496,7 +503,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     for (int c = 0; c < NC; ++c) bufQ[(e * NC + c) * NQ + i] = w[c] * sc;
   }
   __syncthreads();
-  if (proj == 2 && DIM == 3 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED) {
+  if (DIM == 3 && (PROJ_CT == 2 || (proj == 2 && T.v_kind == V_WARPED && T.mass_kind == MASS_WEIGHT_ADJUSTED))) {
     // projected entropy variables at the volume nodes, V M^-1 V^T (W J w) with
     // M^-1 = V^T (W/J) V:  two fused V V^T passes around the W/J scaling, no modal intermediate
 #ifdef SSE_NO_FUSED_SCALE   // A/B knob: two V V^T passes around a scaling pass
@@ -534,7 +541,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     }
     apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   }
-  apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF, rsc);
+  apply_R_t<NQ, NC, E, Nf, N1, (PROJ_CT == 2 && DIM == 3)>(T, bufQ, bufF, rsc);
   // entropy -> conservative variables at the volume nodes (modal case) and the facet nodes,
   // one loop so the log/exp sequence is instantiated once
   const int nvol = (proj == 2) ? Ev * NQ : 0;

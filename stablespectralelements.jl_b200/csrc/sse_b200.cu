@@ -276,6 +276,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     // an element's operators are small and N_q is not a multiple of 16 (a thread per staged row
     // strides by N_q: 16-way bank conflicts for N_q = 16, 64); streaming wins otherwise.
     if (const char* pw = getenv("SSE_B200_PROJ_WARP")) h->proj_warp = atoi(pw);
+    if (const char* rp = getenv("SSE_B200_NODAL_RT_PROJ")) h->nodal_rt_proj = atoi(rp);
     const char* ps = getenv("SSE_B200_PHYS_STAGED");
     const size_t op_bytes = sizeof(double) * ((size_t)cfg->dim * cfg->N_p * cfg->N_q + (size_t)cfg->N_p * cfg->N_f);
     h->phys_staged = ps ? (atoi(ps) == 1) : (cfg->N_q % 16 != 0 && op_bytes <= (size_t)48 * 1024);
@@ -447,6 +448,14 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       }
       if (sep && !getenv("SSE_B200_NO_RSEP")) {
         T.R_ng = (int)gstart.size();
+        // every row a tensor line of n1 terms or one of the separable blocks?  (then loop A's
+        // entropy-projection instantiation compiles only those two row forms)
+        h->r_sep_only = 1;
+        for (int j = 0; j < Nf; ++j) {
+          const int cnt = R.rp[j + 1] - R.rp[j];
+          const bool block = cnt == n1r * n1r && cnt > n1r && ((desc[j] >> 10) & 1023) == 1;
+          if (cnt != n1r && !block) h->r_sep_only = 0;
+        }
         for (int a3 = 0; a3 < 8; ++a3) T.R_r3[a3] = r3[a3];
         if (dev_upload_vec(h, gstart, &T.R_gstart) || dev_upload_vec(h, grp, &T.R_grp) ||
             dev_upload_vec(h, RE, &T.R_E))
@@ -688,7 +697,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
     h->halo_elems = (cfg->N_halo + Nf - 1) / Nf;
     const int64_t ntr = (int64_t)Nf * (Ne + h->halo_elems);
     std::vector<int> toff((size_t)Nf * Ne), mp((size_t)Nf * Ne);
-    h->n_chunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+    h->n_chunk = (int)std::min<int64_t>(SSE_DEFAULT_CHUNKS, std::max<int64_t>(1, Ne / 4096));
     if (const char* ce = getenv("SSE_B200_HOST_CHUNKS"))
       h->n_chunk = (int)std::min<int64_t>(std::min<int64_t>(SSE_MAX_CHUNKS, Ne), std::max(1, atoi(ce)));
     if (h->second_order || cfg->N_halo > 0) h->n_chunk = 1;
@@ -721,7 +730,7 @@ static int create_impl(sse_handle* h, const sse_config* cfg, const sse_operators
       int64_t t = mapP[g];
       if (t < 0 || t >= ntr) return fail("mapP[%lld] = %lld out of range", (long long)g, (long long)t);
       int64_t kp = t / Nf, jp = t % Nf;
-      if (kp < Ne) h->chunk_need[chunk_of(g / Nf)] |= 1u << chunk_of(kp);
+      if (kp < Ne) h->chunk_need[chunk_of(g / Nf)] |= 1ull << chunk_of(kp);
       toff[g] = (int)(kp * Nc * Nf + jp);
       mp[g] = (int)t;
     }
@@ -970,7 +979,7 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
   }
   std::vector<int> b_order;
   int rc = 0;
-  uint32_t a_done = 0, b_done = 0, a_seen = 0;   // a_seen: loop-A events the main stream waited for
+  uint64_t a_done = 0, b_done = 0, a_seen = 0;   // a_seen: loop-A events the main stream waited for
   for (int c = 0; c < nchunk && !rc; ++c) {
     CU(cudaStreamWaitEvent(a_stream, h->ev_chunk[c], 0));
     h->G.k_begin = lo(c);
@@ -979,22 +988,22 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
     rc = run_a(h, h->u);
     h->stream = main_stream;
     if (a_stream != main_stream) CU(cudaEventRecord(h->ev_a[c], a_stream));
-    a_done |= 1u << c;
+    a_done |= 1ull << c;
     for (int b = 0; b < nchunk && !rc; ++b) {
-      if ((b_done >> b) & 1u) continue;
-      const uint32_t need = h->chunk_need[b] | (1u << b);
+      if ((b_done >> b) & 1ull) continue;
+      const uint64_t need = h->chunk_need[b] | (1ull << b);
       if (need & ~a_done) continue;   // a neighbour chunk is missing
       if (a_stream != main_stream)
         for (int n = 0; n < nchunk; ++n)
-          if ((need & ~a_seen) & (1u << n)) {
+          if ((need & ~a_seen) & (1ull << n)) {
             CU(cudaStreamWaitEvent(main_stream, h->ev_a[n], 0));
-            a_seen |= 1u << n;
+            a_seen |= 1ull << n;
           }
       h->G.k_begin = lo(b);
       h->G.N_e = lo(b + 1);
       rc = run_b(h, h->dudt, rk);
       if (rc) break;
-      b_done |= 1u << b;
+      b_done |= 1ull << b;
       // ev_chunk[b] was consumed by loop A of chunk b (b <= c), so it can be reused
       CU(cudaEventRecord(h->ev_chunk[b], h->stream));
       CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_chunk[b], 0));
@@ -1034,7 +1043,7 @@ int sse_upload_and_nodal_values(sse_handle* h, const double* u_host) {
   CU(cudaSetDevice(h->cfg.device));
   const int64_t Ne = h->cfg.N_e;
   const int64_t blk = (int64_t)h->cfg.N_p * h->cfg.N_c;
-  const int nchunk = (int)std::min<int64_t>(SSE_MAX_CHUNKS, std::max<int64_t>(1, Ne / 4096));
+  const int nchunk = (int)std::min<int64_t>(SSE_DEFAULT_CHUNKS, std::max<int64_t>(1, Ne / 4096));
   auto lo = [&](int c) { return (Ne * c) / nchunk; };
   // the copy stream must not overwrite u while earlier work of the main stream still reads it
   CU(cudaEventRecord(h->ev[3], h->stream));

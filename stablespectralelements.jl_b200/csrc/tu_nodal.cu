@@ -28,10 +28,25 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
     }
   }
   const size_t smem = NodalCfg<DIM, N1>::bytes(h->cfg.N_c, h->cfg.N_p, h->cfg.N_f);
-  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)((h->G.N_e - h->G.k_begin + EL - 1) / EL);
   h->G.pf_dist = h->prefetch ? h->sm_count * SSE_NODAL_MINB(DIM, N1) * EL : 0;
+  if constexpr (LAW == LAW_EULER) {
+    // the entropy-projection path of the modal schemes as its own instantiation
+    // (3-D: warped-product V, weight-adjusted mass solver, separable collapsed-face rows of R)
+    const bool warped_wa = h->T.v_kind == V_WARPED && h->T.mass_kind == MASS_WEIGHT_ADJUSTED &&
+                           h->T.R_ng > 0 && h->r_sep_only;
+    if (h->proj == 2 && (DIM == 2 || warped_wa) && !h->nodal_rt_proj) {
+      CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true, 2>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_nodal_tensor<DIM, N1, LAW, true, 2> SSE_LAUNCH(grid, 128, smem, h->stream)(
+          h->T, h->G, h->P, u_dev, h->u_q, h->u_f, 2);
+      h->launches++;
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
+  CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true>,
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_nodal_tensor<DIM, N1, LAW, true> SSE_LAUNCH(grid, 128, smem, h->stream)(
       h->T, h->G, h->P, u_dev, h->u_q, h->u_f, h->proj);
   h->launches++;

@@ -84,6 +84,10 @@ struct sse_shard {
   void* comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_xchg = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  // boundary element ranges of the device-resident flow on their own streams (SSE_B200_SHARD_STREAMS)
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_unpack = nullptr, ev_join[2] = {nullptr, nullptr};
+  int stream_mode = 2;
   int width = 1;   // doubles per trace node of the widest exchange
   // host-buffer flow: interior pieces [cut[i], cut[i+1]) and, per piece, one past the highest
   // INTERIOR element one of its facet nodes reads a trace from
@@ -184,8 +188,12 @@ int sse_shard_destroy(sse_shard* s) {
   if (s->h) cudaSetDevice(s->h->cfg.device);
   if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
   if (s->comm && s->nccl) s->nccl->CommDestroy(s->comm);
-  for (cudaEvent_t e : {s->ev_pack, s->ev_xchg, s->ev_t0, s->ev_t1})
+  for (cudaStream_t a : s->aux)
+    if (a) cudaStreamSynchronize(a);
+  for (cudaEvent_t e : {s->ev_pack, s->ev_xchg, s->ev_t0, s->ev_t1, s->ev_unpack, s->ev_join[0], s->ev_join[1]})
     if (e) cudaEventDestroy(e);
+  for (cudaStream_t a : s->aux)
+    if (a) cudaStreamDestroy(a);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
   if (s->h) sse_destroy(s->h);
   delete s;
@@ -233,10 +241,16 @@ int sse_shard_create(const sse_config* cfg, const sse_operators* ops, const sse_
   if (cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_xchg, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess) {
+      cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s->aux[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s->aux[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_unpack, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming) != cudaSuccess) {
     sse_fail("stream / event creation failed");
     return bail();
   }
+  if (const char* e = getenv("SSE_B200_SHARD_STREAMS")) s->stream_mode = atoi(e);
   if (world > 1) {
     if (load_nccl(&s->nccl)) return bail();
     NcclId id;
@@ -318,6 +332,44 @@ static int shard_flow(sse_shard* s, double* dudt_dev, double* dudt_host) {
     return loop_b(all, false);
   }
   if (sse_halo_pack(h) || exchange_start(s, h->cfg.N_c)) return -1;
+  if (!h->second_order && !dudt_host && s->stream_mode > 0 && s->plan.n_peers > 0 && !boundary.empty()) {
+    // Device-resident flow with the boundary ranges on their own streams.  A boundary range at
+    // N = 8 is a handful of waves of each kernel (Tet p=4, 511 104 elements: 11 616 elements =
+    // 19.6 waves of the flux kernel, 3.9 of the projection), so launched one after the other on
+    // the main stream every one of the six loop-B kernels ends in a partly filled wave.  Here
+    // the two ranges run side by side, and (mode 2) their chain -- unpack, flux, projection --
+    // is ordered behind the EXCHANGE only, not behind the interior kernels: its CTAs fill the
+    // tail waves of the interior launches.  The interior reads no halo slot and the ranges
+    // write disjoint elements (dudt or the fused RK update), so any interleaving is safe; the
+    // main stream joins both at the end.
+    cudaStream_t const main_stream = h->stream;
+    struct Restore { sse_handle* h; cudaStream_t m; ~Restore() { h->stream = m; } } restore{h, main_stream};
+    int rc = 0;
+    if (s->stream_mode >= 2) {
+      CU(cudaStreamWaitEvent(s->aux[0], s->ev_xchg, 0));
+      h->stream = s->aux[0];
+      rc = sse_halo_unpack(h);
+      h->stream = main_stream;
+      if (rc) return -1;
+      CU(cudaEventRecord(s->ev_unpack, s->aux[0]));
+      if (loop_b(interior, false)) return -1;            // overlaps the NVLink transfer
+    } else {
+      if (loop_b(interior, false)) return -1;
+      if (exchange_wait(s) || sse_halo_unpack(h)) return -1;
+      CU(cudaEventRecord(s->ev_unpack, main_stream));
+      CU(cudaStreamWaitEvent(s->aux[0], s->ev_unpack, 0));
+    }
+    for (size_t q = 0; q < boundary.size() && q < 2; ++q) {
+      if (q > 0) CU(cudaStreamWaitEvent(s->aux[q], s->ev_unpack, 0));
+      h->stream = s->aux[q];
+      rc = sse_time_derivative_range(h, dudt_dev, boundary[q].a, boundary[q].b);
+      h->stream = main_stream;
+      if (rc) return -1;
+      CU(cudaEventRecord(s->ev_join[q], s->aux[q]));
+      CU(cudaStreamWaitEvent(main_stream, s->ev_join[q], 0));
+    }
+    return 0;
+  }
   if (!h->second_order) {
     if (loop_b(interior, false)) return -1;            // overlaps the NVLink transfer
     if (exchange_wait(s) || sse_halo_unpack(h)) return -1;

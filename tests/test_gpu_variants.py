@@ -172,3 +172,30 @@ def test_warp_private_projection_matches_the_batched_kernel(monkeypatch):
             d.close()
     assert np.all(np.isfinite(outs[1]))
     assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[0]))
+
+
+@pytest.mark.parametrize("case", ["tet_p4", "tet_p3", "tri_p4"])
+def test_loop_a_projection_instantiation_matches_the_run_time_mode(case, monkeypatch):
+    """Loop A of the modal Euler schemes runs k_nodal_tensor<..., PROJ_CT = 2> (the entropy
+    projection compiled in, the dense-row forms of R left out); SSE_B200_NODAL_RT_PROJ=1 keeps the
+    kernel that takes the mode at run time.  Same stages, same arithmetic: equal up to the FMA
+    contraction choices of two instantiations (the emulator, which has none, sees them bitwise)."""
+    from sse_b200 import device as dev
+    if case == "tri_p4":
+        solver, u0 = cases.euler_tri_case(p=4, M=6, lazy=True)
+    else:
+        solver, u0 = cases.euler_tet_case(p=int(case[-1]), M=3, lazy=True, warp=True, ic="periodic")
+    u = cases.rough_state(solver, u0, seed=11)
+    outs = []
+    for rt in ("0", "1"):
+        monkeypatch.setenv("SSE_B200_NODAL_RT_PROJ", rt)
+        d = dev.DeviceResidual(solver)
+        try:
+            dudt = np.full_like(u, np.nan)
+            d.residual_host(u, dudt)
+            outs.append(dudt)
+        finally:
+            d.close()
+    assert np.all(np.isfinite(outs[0]))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-13 * np.max(np.abs(outs[0]))
+    return outs

@@ -191,6 +191,17 @@ def test_host_pipeline_knobs_in_emulation(emu_lib, monkeypatch):
         {"SSE_B200_HOST_CHUNKS": "9", "SSE_B200_HOST_ASTREAM": "0"}, monkeypatch)
 
 
+@pytest.mark.parametrize("case", ["tet_p4", "tet_p3", "tri_p4"])
+def test_loop_a_projection_instantiation_in_emulation(emu_lib, case, monkeypatch):
+    """Body of tests/test_gpu_variants.py::test_loop_a_projection_instantiation_matches_the_run_time_mode;
+    on the emulator (no FMA contraction differences) the two instantiations are bitwise equal."""
+    import test_gpu_variants as tv
+    emu_lib.emu_launch_log()
+    outs = tv.test_loop_a_projection_instantiation_matches_the_run_time_mode(case, monkeypatch)
+    assert "k_nodal_tensor" in emu_lib.emu_launch_log().decode()
+    assert np.array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("name", ["euler3d_tet_p4_warp_lf", "euler3d_tet_p3_warp_ec"])
 def test_warp_private_projection_in_emulation(emu_lib, name, monkeypatch):
     """k_project_tet_w (one element per warp, __syncwarp between the stages) is bitwise equal to
