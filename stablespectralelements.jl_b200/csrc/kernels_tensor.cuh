@@ -144,6 +144,19 @@ __device__ __noinline__ void apply_V_t(const VTab T, const double* __restrict__ 
   }
 }
 
+// The 3-D warped-product V alone (no run-time choice of the V kind, five table pointers instead of
+// the whole VTab through the call): loop A's entropy-projection instantiation
+template <int N1, int NC, int E, bool OOL>
+__device__ __noinline__ void apply_V3_t(const V3Tab T, const double* __restrict__ src,
+                                        double* __restrict__ dst, double* __restrict__ tmp) {
+  v3_stageC<N1, NC, E>(threadIdx.x, 128, T, src, tmp);
+  __syncthreads();
+  v3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, tmp, dst);
+  __syncthreads();
+  v3_stageA<N1, E * NC>(threadIdx.x, 128, dst);
+  __syncthreads();
+}
+
 // src [E][NC][NQ] -> dst [E][NC][N_p].  The 3-D warped product works in place on src (destroyed).
 template <int DIM, int N1, int NC, int E, bool OOL = false>
 __device__ __noinline__ void apply_Vt_t(const VTab T, double* __restrict__ src,
@@ -244,8 +257,19 @@ __device__ __noinline__ void apply_VtV_t(const VTab T, double* __restrict__ x,
 // the registers of one thread (v3_stageA_scale_At).  sc: [E][NQ].
 // the inner three stages B^T, K, B (in place on x [b1][a2][a3]) are one out-of-line body shared
 // by both halves: loop A is sensitive to its instruction footprint
+#ifndef SSE_NODAL_BTKB_INLINE
+#define SSE_NODAL_BTKB_INLINE 0
+#endif
+#if SSE_NODAL_BTKB_INLINE
+#define SSE_BTKB_ATTR __forceinline__
+#else
+#define SSE_BTKB_ATTR __noinline__
+#endif
+#ifndef SSE_NODAL_OOL
+#define SSE_NODAL_OOL true   // loop A: stage-B bodies out of line (one per b1)
+#endif
 template <int N1, int NC, int E, bool OOL>
-__device__ __noinline__ void apply_BtKB_t(const V3Tab T, double* __restrict__ x,
+__device__ SSE_BTKB_ATTR void apply_BtKB_t(const V3Tab T, double* __restrict__ x,
                                           double* __restrict__ tmp) {
   double* Z2 = tmp + E * NC * V3Dims<N1>::ZS;
   vt3_stageB<N1, E * NC, OOL>(threadIdx.x, 128, x, tmp);
@@ -265,7 +289,7 @@ __device__ __forceinline__ void apply_VtV_scaled_VtV_t(const VTab T, double* __r
   v3_stageA_scale_At<N1, E * NC, NC>(threadIdx.x, 128, x, sc);
   __syncthreads();
   apply_BtKB_t<N1, NC, E, OOL>(T.v3, x, tmp);
-  v3_stageA<N1, E * NC>(threadIdx.x, 128, x);
+  v3_stageA<N1, E * NC>(threadIdx.x, 128, x);   // (one shared out-of-line copy of this stage: +0.8 %)
   __syncthreads();
 }
 
@@ -283,7 +307,7 @@ __device__ __forceinline__ void apply_R_t(const Tables& T, const double* __restr
   // Collapsed face: R[(f1,f2)][a1=f1][a2][a3] = E[f2][a2] r3[a3] (Kronecker factors of
   // tensor_simplex.jl:221-306), so the a3-contraction is shared by the N1 rows of a group:
   // 2 * N1 instead of N1^2 terms per row, and every row of R costs the same.
-  const int ng = T.R_ng;
+  const int ng = SEP_ONLY ? N1 : T.R_ng;   // SEP_ONLY: one group per a1 (launcher: T.R_ng == N1)
   if (SEP_ONLY || ng > 0) {
     SSE_LOOP(idx, E * NC * ng * N1) {
       const int a2 = idx % N1, g = (idx / N1) % ng, ec = idx / (N1 * ng);
@@ -480,7 +504,10 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     if (proj == 2 && threadIdx.x < E * NQ) scq[threadIdx.x] = fdiv(__ldg(T.W + threadIdx.x % NQ), jq);
   }
   __syncthreads();
-  apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
+  if constexpr (PROJ_CT == 2 && DIM == 3)
+    apply_V3_t<N1, NC, E, SSE_NODAL_OOL>(V3Tab{T.wC, T.wCt, T.pairtab, T.modetab, T.wK}, bufP, bufQ, tmp);
+  else
+    apply_V_t<DIM, N1, NC, E, true>(vtab(T), bufP, bufQ, tmp);
   if (proj == 0) {
     apply_R_t<NQ, NC, E, Nf, N1>(T, bufQ, bufF, rsc);
     SSE_LOOP(idx, Ev * NC * NQ) u_q[k0 * NC * NQ + idx] = bufQ[idx];
@@ -516,7 +543,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     __syncthreads();
     if constexpr (DIM == 3) apply_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp);
 #else
-    if constexpr (DIM == 3) apply_VtV_scaled_VtV_t<N1, NC, E, true>(vtab(T), bufQ, tmp, scq);
+    if constexpr (DIM == 3) apply_VtV_scaled_VtV_t<N1, NC, E, SSE_NODAL_OOL>(vtab(T), bufQ, tmp, scq);
 #endif
   } else if (proj == 2) {
     apply_Vt_t<DIM, N1, NC, E, true>(vtab(T), bufQ, bufP, tmp);
@@ -549,7 +576,7 @@ k_nodal_tensor(Tables T, Geo G, Phys P, const double* __restrict__ u, double* __
     const bool vol = idx < nvol;
     const int ii = vol ? idx : idx - nvol;
     const int npt = vol ? NQ : Nf;
-    const int pt = ii % npt, e = ii / npt;
+    const int pt = E == 1 ? ii : ii % npt, e = E == 1 ? 0 : ii / npt;
     const double* srcw = vol ? bufQ : bufF;
     double w[NC], uu[NC];
 #pragma unroll

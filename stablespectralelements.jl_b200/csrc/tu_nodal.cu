@@ -34,7 +34,7 @@ static int launch_a_fast(sse_handle* h, const double* u_dev) {
     // the entropy-projection path of the modal schemes as its own instantiation
     // (3-D: warped-product V, weight-adjusted mass solver, separable collapsed-face rows of R)
     const bool warped_wa = h->T.v_kind == V_WARPED && h->T.mass_kind == MASS_WEIGHT_ADJUSTED &&
-                           h->T.R_ng > 0 && h->r_sep_only;
+                           h->T.R_ng == N1 && h->r_sep_only;
     if (h->proj == 2 && (DIM == 2 || warped_wa) && !h->nodal_rt_proj) {
       CU(cudaFuncSetAttribute(k_nodal_tensor<DIM, N1, LAW, true, 2>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

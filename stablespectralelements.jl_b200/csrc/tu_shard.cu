@@ -87,7 +87,7 @@ struct sse_shard {
   // boundary element ranges of the device-resident flow on their own streams (SSE_B200_SHARD_STREAMS)
   cudaStream_t aux[2] = {nullptr, nullptr};
   cudaEvent_t ev_unpack = nullptr, ev_join[2] = {nullptr, nullptr};
-  int stream_mode = 2;
+  int stream_mode = 1;
   int width = 1;   // doubles per trace node of the widest exchange
   // host-buffer flow: interior pieces [cut[i], cut[i+1]) and, per piece, one past the highest
   // INTERIOR element one of its facet nodes reads a trace from
@@ -336,12 +336,17 @@ static int shard_flow(sse_shard* s, double* dudt_dev, double* dudt_host) {
     // Device-resident flow with the boundary ranges on their own streams.  A boundary range at
     // N = 8 is a handful of waves of each kernel (Tet p=4, 511 104 elements: 11 616 elements =
     // 19.6 waves of the flux kernel, 3.9 of the projection), so launched one after the other on
-    // the main stream every one of the six loop-B kernels ends in a partly filled wave.  Here
-    // the two ranges run side by side, and (mode 2) their chain -- unpack, flux, projection --
-    // is ordered behind the EXCHANGE only, not behind the interior kernels: its CTAs fill the
-    // tail waves of the interior launches.  The interior reads no halo slot and the ranges
-    // write disjoint elements (dudt or the fused RK update), so any interleaving is safe; the
-    // main stream joins both at the end.
+    // the main stream every one of the six loop-B kernels ends in a partly filled wave.  Mode 1
+    // (default): the two ranges run side by side once the interior is queued and the halo is
+    // unpacked.  Mode 2: their chain -- unpack, flux, projection -- is ordered behind the
+    // EXCHANGE only, not behind the interior kernels, and fills the interior's tail waves.
+    // The interior reads no halo slot and the ranges write disjoint elements (dudt or the fused
+    // RK update), so any interleaving is safe; the main stream joins both at the end.
+    // Measured on 2 B200 (profiles/r2_ab_log.md, sessions AC / AD): Euler Tet p=4, 65 856
+    // elements per rank (the N = 8 shard size): 2.239 -> 2.216 (mode 1) / 2.208 ms (mode 2);
+    // config 3, 65 856 elements per rank: 0.475 -> 0.437 ms (mode 1).  One projection launch
+    // over the whole shard after the flux kernels of all ranges (mode "3") was slower (2.25 ms):
+    // the short projection launches overlap with the other ranges' flux kernels, removed.
     cudaStream_t const main_stream = h->stream;
     struct Restore { sse_handle* h; cudaStream_t m; ~Restore() { h->stream = m; } } restore{h, main_stream};
     int rc = 0;

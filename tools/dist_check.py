@@ -19,6 +19,8 @@ worst = 0.0
 for name, (solver, u0) in {
         "euler_tet_p4_warp": cases.euler_tet_case(p=4, M=4, lazy=True, warp=True, ic="periodic"),
         "euler_tri_p4": cases.euler_tri_case(p=4, M=8, lazy=True),
+        # config 3: scalar standard form on tetrahedra (k_standard_tensor + the batched projection)
+        "adv_tet_p4": cases.advection_tet_case(p=4, M=4, lazy=True),
         # second-order (BR1): two halo exchanges, u_f then q_f
         "advdiff1d_p4_br1": cases.advection_diffusion_case(d=1, p=4, M=16, lazy=True),
         "advdiff2d_p3_br1": cases.advection_diffusion_case(d=2, p=3, M=8, lazy=True)}.items():
