@@ -454,8 +454,11 @@ struct NodalCfg {
 // kernel is latency-bound: Tet p=4 gains 2 % at 12 CTAs (40 registers, 8 bytes of spill) over 10
 // and loses 4 % at 16 (32 registers, 56 bytes); the other instantiations spill more at 40
 // registers and stay at 10 (profiles/r2_ab_log.md).
+#ifndef SSE_NODAL_MINB_T5
+#define SSE_NODAL_MINB_T5 12
+#endif
 #ifndef SSE_NODAL_MINB
-#define SSE_NODAL_MINB(DIM, N1) (((DIM) == 3 && (N1) == 5) ? 12 : 10)
+#define SSE_NODAL_MINB(DIM, N1) (((DIM) == 3 && (N1) == 5) ? SSE_NODAL_MINB_T5 : 10)
 #endif
 
 // PROJ_CT: -1 = the projection mode is the run-time argument; 2 = compiled for the entropy

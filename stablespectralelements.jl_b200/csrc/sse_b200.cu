@@ -967,11 +967,13 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
     cudaEventRecord(e, st);
     tev.push_back(e);
   };
-  // SSE_B200_HOST_NOCOPY=1 (diagnostic): the chunked kernel schedule without the copies
-  static const bool nocopy = [] { const char* e = getenv("SSE_B200_HOST_NOCOPY"); return e && atoi(e) == 1; }();
+  // SSE_B200_HOST_NOCOPY (diagnostic): the chunked kernel schedule without the copies (1), without
+  // the downloads only (2), without the uploads only (3)
+  static const int nocopy_mode = [] { const char* e = getenv("SSE_B200_HOST_NOCOPY"); return e ? atoi(e) : 0; }();
+  const bool no_h2d = nocopy_mode == 1 || nocopy_mode == 3, no_d2h = nocopy_mode == 1 || nocopy_mode == 2;
   mark(h->copy_stream);                       // [0] start
   for (int c = 0; c < nchunk; ++c) {
-    if (!nocopy)
+    if (!no_h2d)
     CU(cudaMemcpyAsync(h->u + lo(c) * blk, u + lo(c) * blk, (lo(c + 1) - lo(c)) * blk * sizeof(double),
                        cudaMemcpyHostToDevice, h->copy_stream));
     CU(cudaEventRecord(h->ev_chunk[c], h->copy_stream));
@@ -1008,7 +1010,7 @@ int sse_residual(sse_handle* h, const double* u, double* dudt, double t, int whe
       CU(cudaEventRecord(h->ev_chunk[b], h->stream));
       CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_chunk[b], 0));
       mark(h->stream);                        // loop B of chunk b done
-      if (!nocopy)
+      if (!no_d2h)
       CU(cudaMemcpyAsync(dudt + lo(b) * blk, h->dudt + lo(b) * blk,
                          (lo(b + 1) - lo(b)) * blk * sizeof(double), cudaMemcpyDeviceToHost,
                          h->d2h_stream));
