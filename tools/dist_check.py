@@ -47,6 +47,30 @@ for name, (solver, u0) in {
             print(f"{name} [{backend}]: world={world} max rel err over ranks = {t.item():.3e}, host path "
                   f"bitwise = {same} (interior {d.part.interior}, halo {d.part.n_halo})", flush=True)
         worst = max(worst, t.item())
+        # low-storage RK step on the shards (sse_shard_rk_step_ck54: the update fused into the
+        # epilogue of every loop-B range of the flow) against the single-handle step
+        if backend == "library" and name in ("euler_tet_p4_warp", "adv_tet_p4", "euler_tri_p4"):
+            from sse_b200.device import DeviceResidual
+            dt = 1e-4
+            d.set_state(u[d.elements])
+            for _ in range(2):
+                d.dev.shard_rk_step_ck54(dt)
+            d.sync()
+            got = d.dev.get_state()
+            one = DeviceResidual(solver, device=lr)
+            one.set_state(u)
+            for _ in range(2):
+                one.rk_step_ck54(dt)
+            one.sync()
+            want = one.get_state()[d.elements]
+            one.close()
+            e3 = torch.tensor([float(np.max(np.abs(got - want)) / np.max(np.abs(want)))],
+                              device="cuda", dtype=torch.float64)
+            dist.all_reduce(e3, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"{name} [library]: two sharded CK54 steps vs single handle: max rel diff "
+                      f"{e3.item():.3e}", flush=True)
+            worst = max(worst, e3.item())
         d.close()
 dist.barrier()
 dist.destroy_process_group()
