@@ -520,7 +520,7 @@ def main():
                 "traffic_source": TRAFFIC_SOURCE,
                 "peak_source": "FP64 DFMA-chain peak measured in this run "
                                "(sse_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 figure)",
-                "loop_a": {"kernel": "k_nodal_tensor<3,5,Euler>", "ms": split["loop_a_ms"],
+                "loop_a": {"kernel": "k_nodal_tensor<3,5,Euler,PROJ_CT=2>", "ms": split["loop_a_ms"],
                            "fp64_frac": FLOP_PER_ELT["loop_a"] * n_loc_e / ta / 1e12 / fp64_peak},
                 "whole_residual_tflops": FLOP_PER_ELT["residual"] * n_loc_e / (ta + tb) / 1e12,
             }
