@@ -150,13 +150,16 @@ def test_one_element_tet_kernels_in_emulation(emu_lib, name, p, monkeypatch):
         d.close()
 
 
-@pytest.mark.parametrize("chunks,taper", [(9, "1"), (9, "0"), (32, "1")])
+@pytest.mark.parametrize("chunks,taper", [(9, "1"), (9, "0"), (32, "1"), (48, "1"), (64, "0")])   # > 32: the 64-bit chunk masks
 def test_host_buffer_pipeline_with_tapered_chunks(emu_lib, chunks, taper, monkeypatch):
     """sse_residual(where=HOST) cut into element chunks of unequal size (small first and last
     chunks, SSE_B200_HOST_TAPER) with the dependency-driven loop-B order: bitwise equal to the
     device-resident residual of the same handle."""
     monkeypatch.setenv("SSE_B200_HOST_TAPER", taper)
-    solver, u0 = CASES["euler2d_tri_p4_lf"][0]()
+    if chunks > 32:   # 72 elements, so that more than 32 chunks exist
+        solver, u0 = cases.euler_tri_case(p=4, M=6, lazy=True)
+    else:
+        solver, u0 = CASES["euler2d_tri_p4_lf"][0]()
     u = cases.rough_state(solver, u0, seed=3)
     out = []
     for n in (chunks, 1):
