@@ -51,7 +51,8 @@ def main():
     from sse_b200 import device as dev
     from sse_b200 import problems as cases
     from sse_b200.distributed import DistributedResidual
-    lib = dev.load_library(build_emu.build(), allow_emulation=True)
+    # SSE_EMU_ASAN=1: the AddressSanitizer build (every "device" buffer its own heap block)
+    lib = dev.load_library(build_emu.build(asan=os.environ.get("SSE_EMU_ASAN") == "1"), allow_emulation=True)
     assert lib.sse_version() < 0
     dev._LIB = lib
     solver, u0 = problem(case)

@@ -23,15 +23,18 @@ WORKER = os.path.join(HERE, "emu", "shard_worker.py")
 sys.path.insert(0, os.path.join(HERE, "emu"))
 
 
-def _run_world(case, world, mode):
+def _run_world(case, world, mode, asan_rt=None):
     import shard_worker
     shard_worker.build_fake_nccl()          # once, before the ranks race for it
     import build_emu
-    build_emu.build()
+    build_emu.build(asan=asan_rt is not None)
     tmp = tempfile.mkdtemp(prefix="sse_shard_")
     try:
-        env = dict(os.environ, SSE_B200_SHARD_STREAMS=str(mode), FAKE_NCCL_TIMEOUT_S="200")
+        env = dict(os.environ, SSE_B200_SHARD_STREAMS=str(mode), FAKE_NCCL_TIMEOUT_S="400")
         env.pop("SSE_B200_LIB", None)
+        if asan_rt:
+            env.update(SSE_EMU_ASAN="1", LD_PRELOAD=asan_rt,
+                       ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=0")
         procs = [subprocess.Popen([sys.executable, WORKER, str(r), str(world), tmp, case,
                                    os.path.join(tmp, f"out{r}.npz")], env=env,
                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
@@ -44,6 +47,7 @@ def _run_world(case, world, mode):
                 for q in procs:
                     q.kill()
                 raise
+            assert "ERROR: AddressSanitizer" not in log.decode(), log.decode()[-3000:]
             assert p.returncode == 0, log.decode()[-3000:]
         for r in range(world):
             outs.append(dict(np.load(os.path.join(tmp, f"out{r}.npz"))))
@@ -114,3 +118,18 @@ def test_library_sharded_flow_on_cpu(single_handle, case, world, mode):
     if case != "advdiff2d_p3_br1" and world == 2:
         # the flow under test needs an interior AND both boundary ranges on at least one rank
         assert any(0 < o["interior"][0] < o["interior"][1] < len(o["elements"]) for o in outs)
+
+
+@pytest.mark.parametrize("case,world,mode", [("euler_tri_p4", 2, 1), ("adv_tet_p2", 2, 2)])
+def test_library_sharded_flow_address_sanitizer(single_handle, case, world, mode):
+    """The same run on the AddressSanitizer build of the emulated library: every "device" buffer
+    (state, traces with their halo slots, send / receive buffers) is its own heap block, so an
+    out-of-range halo slot, send index or element range of the sharded flow is trapped."""
+    asan_rt = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
+                             text=True).stdout.strip()
+    if not os.path.isabs(asan_rt) or not os.path.exists(asan_rt):
+        pytest.skip("libasan not available")
+    dudt1, _, _ = single_handle(case)
+    for o in _run_world(case, world, mode, asan_rt=asan_rt):
+        assert np.array_equal(o["dudt"], dudt1[o["elements"]])
+        assert np.array_equal(o["dudt_host"], dudt1[o["elements"]])
